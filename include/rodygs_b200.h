@@ -1,0 +1,203 @@
+/*
+ * rodygs_b200 — C ABI of the B200-native dynamic-splatting hot path.
+ *
+ * This is the drop-in boundary for the native module the reference imports as
+ * `diff_gauss_pose` (un-vendored submodule, /root/reference/.gitmodules:1-4).
+ * The reference reaches that module only through
+ *   GaussianRasterizationSettings(...)      /root/reference/src/trainer/renderer.py:50-63
+ *   GaussianRasterizer(...)(means3D=...)    /root/reference/src/trainer/renderer.py:65-101
+ * (twins at src/model/rodygs_static.py:221-281 and src/evaluator/eval.py:118-176);
+ * upstream binds it with pybind11 (`_C.rasterize_gaussians`,
+ * `_C.rasterize_gaussians_backward`).  The entry points below are what that
+ * binding would call instead; rodygs_b200/_lib.py loads them with ctypes.
+ *
+ * Conventions
+ *  - plain C: raw device pointers, sizes, a cudaStream_t passed as void*.
+ *  - every function returns 0 on success; otherwise a negative RDG_E_* code and
+ *    rdg_last_error() (thread-local) describes the failure.
+ *  - the library owns no device memory; every buffer (inputs, outputs,
+ *    workspaces) is allocated by the caller (torch's caching allocator).
+ *  - all launches go to the given stream; no call synchronises the host.
+ *  - matrices are passed the way the reference passes them: "glm storage",
+ *    i.e. the 16 floats of M^T row-major == M column-major
+ *    (renderer.py:57 `projection_matrix.transpose(0, 1)`, :97-99 viewmatrix).
+ *  - float = IEEE binary32 everywhere.
+ */
+#ifndef RODYGS_B200_H
+#define RODYGS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDG_ABI_VERSION 1
+#define RDG_TILE 16
+#define RDG_NUM_BASIS_MAX 16
+
+enum {
+    RDG_OK = 0,
+    RDG_E_ARG = -1,      /* bad argument (null pointer, size, unsupported option) */
+    RDG_E_CUDA = -2,     /* a CUDA runtime call / launch failed */
+    RDG_E_CAPACITY = -3  /* workspace smaller than rdg_*_workspace_bytes() says */
+};
+
+/* One set of Gaussians.  For the drop-in boundary (already activated, already
+ * concatenated tensors: renderer.py:88-100) only `st` is used with
+ * n_dynamic = 0 and raw = 0.  For the fused path (raw parameters, static and
+ * dynamic models never concatenated: replaces rodygs.py:68-113 +
+ * rodygs_static.py:82-105 + rodygs_dynamic.py:122-138) `st` is the static
+ * model, `dy` the dynamic one, raw = 1. */
+typedef struct RdgSet {
+    const float* xyz;       /* [n,3] */
+    const float* scaling;   /* [n,3]  raw: log-scale; activated: scale */
+    const float* rotation;  /* [n,4]  (r,x,y,z) raw: un-normalised */
+    const float* opacity;   /* [n,1]  raw: logit; activated: opacity */
+    const float* sh_dc;     /* [n, sh_dc_stride]   first 3 floats = degree-0 coefficients (r,g,b) */
+    const float* sh_rest;   /* [n, sh_rest_stride] first 3*(K-1) floats = higher coefficients, coefficient-major */
+    int32_t sh_dc_stride;   /* floats between consecutive Gaussians (3 for _features_dc, 48 for a cat'ed [n,16,3]) */
+    int32_t sh_rest_stride; /* 45 for _features_rest, 48 for a cat'ed [n,16,3] (pointer = base + 3) */
+} RdgSet;
+
+typedef struct RdgScene {
+    int64_t n_static;
+    int64_t n_dynamic;
+    RdgSet st;
+    RdgSet dy;
+    int32_t raw;                 /* 1: apply exp / normalize / sigmoid inside the kernel */
+    const float* colors_precomp; /* [N,3] or NULL; if set, SH is ignored (renderer.py:78-83) */
+    /* time-conditioned deformation of the dynamic set (raw = 1 only) */
+    int32_t use_deform;          /* rodygs.py:69-73 `use_deform` */
+    int32_t num_basis;           /* <= RDG_NUM_BASIS_MAX */
+    int32_t num_times;           /* T */
+    const float* motion_coeff;   /* [n_dynamic, num_basis]  (_motion_coeff [n,1,K]) */
+    const int32_t* time_ind;     /* [n_dynamic] birth-frame index (gaussian_to_time_ind) */
+    const float* basis_t;        /* [num_basis,7]  B(t) for this view's time */
+    const float* table;          /* [T,num_basis,7] B at every training time (get_total_motion_table) */
+    float spatial_lr_scale;
+} RdgScene;
+
+typedef struct RdgView {
+    int32_t height, width;
+    float tanfovx, tanfovy;
+    float scale_modifier;
+    int32_t sh_degree;           /* 0..3 */
+    int32_t enable_cov_grad;     /* pose gradient through the covariance path */
+    int32_t enable_sh_grad;      /* pose gradient through the camera position (SH view direction) */
+    const float* viewmatrix;     /* device, 16 floats, glm storage */
+    const float* projmatrix;     /* device, 16 floats, glm storage (perspective only, renderer.py:57) */
+    const float* bg;             /* device, 3 floats */
+} RdgView;
+
+/* Per-Gaussian screen-space state written by preprocess, read by binning,
+ * blend and the backward pass.  All arrays have N = n_static + n_dynamic rows. */
+typedef struct RdgGeom {
+    int32_t* radii;          /* [N]   0 = culled */
+    uint32_t* tiles_touched; /* [N] */
+    float* p0;               /* [N,4] px, py, conic A, conic B */
+    float* p1;               /* [N,4] conic C, opacity, r, g */
+    float* p2;               /* [N,2] b, view-space depth */
+    uint8_t* clamped;        /* [N]   bit c set = channel c clamped at 0 */
+    float* dbg_activated;    /* optional [N,11] (xyz, scale, quat, opacity) as used by the kernel; NULL to skip */
+} RdgGeom;
+
+/* Tile-binning result. */
+typedef struct RdgBins {
+    uint64_t* keys_sorted;   /* [D_cap] (tile << 32) | float_bits(depth) */
+    uint32_t* vals_sorted;   /* [D_cap] Gaussian id */
+    uint32_t* ranges;        /* [tiles,2] [start,end) */
+    uint32_t* point_offsets; /* [N] inclusive scan of tiles_touched */
+    uint32_t* num_rendered;  /* [2]: [0] = D (sum tiles_touched), [1] = 1 if D > D_cap (nothing past D_cap is written) */
+    uint64_t* keys_unsorted; /* optional [D_cap] for tests; NULL to use workspace */
+    uint32_t* vals_unsorted; /* optional [D_cap] */
+} RdgBins;
+
+typedef struct RdgImage {
+    float* color;        /* [3,H,W] */
+    float* depth;        /* [1,H,W] */
+    float* alpha;        /* [1,H,W] */
+    float* final_T;      /* [H,W] */
+    uint32_t* n_contrib; /* [H,W] */
+} RdgImage;
+
+/* Gradients w.r.t. one RdgSet (same shapes/strides as the inputs). NULL = skip. */
+typedef struct RdgSetGrad {
+    float* xyz; float* scaling; float* rotation; float* opacity; float* sh_dc; float* sh_rest;
+} RdgSetGrad;
+
+typedef struct RdgSceneGrad {
+    RdgSetGrad st;
+    RdgSetGrad dy;
+    float* colors_precomp;   /* [N,3] or NULL */
+    float* means2D;          /* [N,3] gradient sink (renderer.py:38-44), per NDC unit; z column = 0 */
+    float* viewmatrix;       /* [16] glm storage, accumulated (+=): zero it before the call */
+    float* motion_coeff;     /* [n_dynamic,num_basis] */
+    float* table;            /* [T,num_basis,7] accumulated (+=) */
+    float* basis_t;          /* [num_basis,7]   accumulated (+=) */
+} RdgSceneGrad;
+
+int rdg_abi_version(void);
+const char* rdg_last_error(void);
+
+/* ---- forward ------------------------------------------------------------ */
+
+/* deformation + activations + EWA projection + SH->RGB. */
+int rdg_preprocess_fwd(const RdgScene* scene, const RdgView* view, const RdgGeom* geom, void* stream);
+
+/* bytes of scratch rdg_bin needs for N Gaussians and at most d_cap duplicates. */
+int64_t rdg_bin_workspace_bytes(int64_t n, int64_t d_cap, int32_t height, int32_t width);
+
+/* scan + duplicateWithKeys + radix sort + identifyTileRanges (§8 a8). */
+int rdg_bin(int64_t n, const RdgGeom* geom, int32_t height, int32_t width, int64_t d_cap,
+            const RdgBins* bins, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* front-to-back alpha blend of colour, depth and alpha (§8 a9). */
+int rdg_blend_fwd(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view,
+                  const RdgImage* out, void* stream);
+
+/* ---- backward ------------------------------------------------------------- */
+
+/* reverse-order blend backward (§8 a10): accumulates per-Gaussian screen-space
+ * gradients into acc [N,12] = (dpx, dpy, dA, dB, dC, dopacity, dr, dg, db, ddepth, 0, 0);
+ * acc must be zeroed by the caller.  dL_dcolor/depth/alpha may be NULL. */
+int rdg_blend_bwd(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view,
+                  const RdgImage* fwd, const float* dL_dcolor, const float* dL_ddepth,
+                  const float* dL_dalpha, float* acc, void* stream);
+
+/* acc -> parameter gradients (+ pose, + deformation) (§8 a10, App. A.7). */
+int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, const RdgGeom* geom,
+                       const float* acc, const RdgSceneGrad* grads, void* stream);
+
+/* ---- losses ----------------------------------------------------------------- */
+
+int64_t rdg_l1_dssim_workspace_bytes(int32_t channels, int32_t height, int32_t width);
+
+/* loss = w_l1 * mean|x-y| + w_dssim * (1 - mean SSIM(x,y))   (loss_utils.py:19-20,57-97;
+ * losses.py:61-107).  out_loss (device, 3 floats) = {loss, l1, ssim}; it must be zeroed
+ * by the caller.  dL_dpred [C,H,W] receives d loss / d pred (may be NULL: forward only). */
+int rdg_l1_dssim(const float* pred, const float* gt, int32_t channels, int32_t height, int32_t width,
+                 float w_l1, float w_dssim, float* out_loss, float* dL_dpred,
+                 void* workspace, int64_t workspace_bytes, void* stream);
+
+/* 1 - Pearson(pred, gt) with the unbiased std (loss_utils.py:100-117), over n_boxes boxes
+ * given as (row0, col0, rows, cols) int32 quadruples on the device; box 0 = the whole image
+ * gives GlobalPearsonDepthLoss, 128x128 boxes give LocalPearsonDepthLoss (losses.py:110-182).
+ * out_loss[b] = per-box loss; dL_dpred (+=) receives sum_b box_weight[b] * d loss_b / d pred
+ * and must be zeroed (or hold another gradient) before the call.
+ * stats: device scratch, 8 doubles per box. */
+int rdg_pearson(const float* pred, const float* gt, int32_t height, int32_t width,
+                const int32_t* boxes, const float* box_weight, int32_t n_boxes, float eps,
+                float* out_loss, float* dL_dpred, double* stats, void* stream);
+
+/* ---- optimiser (next row) ------------------------------------ */
+
+/* In-place Adam over a flat fp32 parameter range (rodygs_static.py:106-149 uses
+ * torch.optim.Adam, eps 1e-15, one lr per group). step >= 1. */
+int rdg_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+             float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RODYGS_B200_H */

@@ -1,0 +1,130 @@
+"""ctypes binding of librodygs_b200.so (the C ABI in include/rodygs_b200.h).
+
+There is no CPU fallback: if the shared library is missing or cannot be
+loaded, importing the product path raises immediately.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librodygs_b200.so")
+
+c_float_p = C.c_void_p  # raw device pointers travel as integers
+c_ptr = C.c_void_p
+
+
+class RdgSet(C.Structure):
+    _fields_ = [("xyz", c_ptr), ("scaling", c_ptr), ("rotation", c_ptr), ("opacity", c_ptr),
+                ("sh_dc", c_ptr), ("sh_rest", c_ptr), ("sh_dc_stride", C.c_int32), ("sh_rest_stride", C.c_int32)]
+
+
+class RdgScene(C.Structure):
+    _fields_ = [("n_static", C.c_int64), ("n_dynamic", C.c_int64), ("st", RdgSet), ("dy", RdgSet),
+                ("raw", C.c_int32), ("colors_precomp", c_ptr), ("use_deform", C.c_int32),
+                ("num_basis", C.c_int32), ("num_times", C.c_int32), ("motion_coeff", c_ptr),
+                ("time_ind", c_ptr), ("basis_t", c_ptr), ("table", c_ptr), ("spatial_lr_scale", C.c_float)]
+
+
+class RdgView(C.Structure):
+    _fields_ = [("height", C.c_int32), ("width", C.c_int32), ("tanfovx", C.c_float), ("tanfovy", C.c_float),
+                ("scale_modifier", C.c_float), ("sh_degree", C.c_int32), ("enable_cov_grad", C.c_int32),
+                ("enable_sh_grad", C.c_int32), ("viewmatrix", c_ptr), ("projmatrix", c_ptr), ("bg", c_ptr)]
+
+
+class RdgGeom(C.Structure):
+    _fields_ = [("radii", c_ptr), ("tiles_touched", c_ptr), ("p0", c_ptr), ("p1", c_ptr), ("p2", c_ptr),
+                ("clamped", c_ptr), ("dbg_activated", c_ptr)]
+
+
+class RdgBins(C.Structure):
+    _fields_ = [("keys_sorted", c_ptr), ("vals_sorted", c_ptr), ("ranges", c_ptr), ("point_offsets", c_ptr),
+                ("num_rendered", c_ptr), ("keys_unsorted", c_ptr), ("vals_unsorted", c_ptr)]
+
+
+class RdgImage(C.Structure):
+    _fields_ = [("color", c_ptr), ("depth", c_ptr), ("alpha", c_ptr), ("final_T", c_ptr), ("n_contrib", c_ptr)]
+
+
+class RdgSetGrad(C.Structure):
+    _fields_ = [("xyz", c_ptr), ("scaling", c_ptr), ("rotation", c_ptr), ("opacity", c_ptr),
+                ("sh_dc", c_ptr), ("sh_rest", c_ptr)]
+
+
+class RdgSceneGrad(C.Structure):
+    _fields_ = [("st", RdgSetGrad), ("dy", RdgSetGrad), ("colors_precomp", c_ptr), ("means2D", c_ptr),
+                ("viewmatrix", c_ptr), ("motion_coeff", c_ptr), ("table", c_ptr), ("basis_t", c_ptr)]
+
+
+# every symbol include/rodygs_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "rdg_abi_version": (C.c_int, []),
+    "rdg_last_error": (C.c_char_p, []),
+    "rdg_preprocess_fwd": (C.c_int, [C.POINTER(RdgScene), C.POINTER(RdgView), C.POINTER(RdgGeom), c_ptr]),
+    "rdg_bin_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
+    "rdg_bin": (C.c_int, [C.c_int64, C.POINTER(RdgGeom), C.c_int32, C.c_int32, C.c_int64, C.POINTER(RdgBins),
+                          c_ptr, C.c_int64, c_ptr]),
+    "rdg_blend_fwd": (C.c_int, [C.c_int64, C.POINTER(RdgGeom), C.POINTER(RdgBins), C.POINTER(RdgView),
+                                C.POINTER(RdgImage), c_ptr]),
+    "rdg_blend_bwd": (C.c_int, [C.c_int64, C.POINTER(RdgGeom), C.POINTER(RdgBins), C.POINTER(RdgView),
+                                C.POINTER(RdgImage), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "rdg_preprocess_bwd": (C.c_int, [C.POINTER(RdgScene), C.POINTER(RdgView), C.POINTER(RdgGeom), c_ptr,
+                                     C.POINTER(RdgSceneGrad), c_ptr]),
+    "rdg_l1_dssim_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "rdg_l1_dssim": (C.c_int, [c_ptr, c_ptr, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, c_ptr, c_ptr,
+                               c_ptr, C.c_int64, c_ptr]),
+    "rdg_pearson": (C.c_int, [c_ptr, c_ptr, C.c_int32, C.c_int32, c_ptr, c_ptr, C.c_int32, C.c_float, c_ptr, c_ptr,
+                              c_ptr, c_ptr]),
+    "rdg_adam": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
+                           C.c_int32, C.c_float, c_ptr]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library (once). Raises if it is not built - there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing. Build it with `python -m rodygs_b200.build` (needs nvcc); "
+            "rodygs_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rdg_abi_version() != 1:
+        raise RuntimeError("librodygs_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().rdg_last_error()
+        raise RuntimeError(f"rodygs_b200 error {rc}: {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("rodygs_b200 runs on CUDA tensors only (no CPU fallback)")
+        if t.dtype not in (torch.float32, torch.int32, torch.int64, torch.uint8):
+            raise RuntimeError(f"unsupported dtype {t.dtype}")

@@ -1,0 +1,275 @@
+// Fused photometric loss  w_l1 * L1 + w_dssim * (1 - SSIM)  with its gradient, the
+// Pearson depth regulariser over boxes, and a flat fused Adam step.
+// SURVEY.md §8 rows a11, a12 (+ f1); spec == oracle/loss_oracle.py, which is pinned
+// against /root/reference/src/utils/loss_utils.py by tests/golden/losses.npz.
+//
+// SSIM: 11-tap separable Gaussian (sigma 1.5, zero padding 5, per channel).  Pass 1
+// blurs (x, y, x^2, y^2, xy) of a 16x16 tile from a 26x26 halo in shared memory, forms
+// the SSIM map and its three partial-derivative maps; pass 2 blurs those maps and
+// applies the chain rule.  HBM-bound: 24 B/px read + 36 B/px maps written, then
+// 36 + 24 B/px read + 12 B/px written (the reference's conv2d chain moves ~700 B/px).
+#include <math.h>
+#include "common.cuh"
+
+#define LT 16            // output tile
+#define HALO 5
+#define LH (LT + 2 * HALO)  // 26
+
+// /root/reference/src/utils/loss_utils.py:34-41: float32 taps exp(-(i-5)^2 / (2*1.5^2)) / sum,
+// evaluated the way the reference does (torch.Tensor of Python floats, divided by its float32 sum).
+__constant__ float c_taps[11] = {1.028380124e-03f, 7.598758209e-03f, 3.600077331e-02f, 1.093606874e-01f,
+                                 2.130055279e-01f, 2.660117149e-01f, 2.130055279e-01f, 1.093606874e-01f,
+                                 3.600077331e-02f, 7.598758209e-03f, 1.028380124e-03f};
+
+template <int Q>
+__device__ __forceinline__ void blur_tile(float (*halo)[LH][LH + 1], float (*hz)[LH][LT], float* out) {
+    // horizontal: LH rows x LT cols
+    for (int idx = threadIdx.x; idx < LH * LT; idx += RDG_BLOCK) {
+        const int r = idx / LT, c = idx % LT;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) s = __fmaf_rn(c_taps[k], halo[q][r][c + k], s);
+            hz[q][r][c] = s;
+        }
+    }
+    __syncthreads();
+    const int r = threadIdx.x / LT, c = threadIdx.x % LT;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; ++k) s = __fmaf_rn(c_taps[k], hz[q][r + k][c], s);
+        out[q] = s;
+    }
+}
+
+__global__ void __launch_bounds__(RDG_BLOCK) ssim_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                             int H, int W, float* __restrict__ map_mu,
+                                                             float* __restrict__ map_s1, float* __restrict__ map_s12,
+                                                             double* __restrict__ sums) {
+    __shared__ float halo[5][LH][LH + 1];
+    __shared__ float hz[5][LH][LT];
+    __shared__ float red[2][RDG_BLOCK / 32];
+    const int ch = blockIdx.z;
+    const size_t plane = (size_t)ch * H * W;
+    const int x0 = blockIdx.x * LT - HALO, y0 = blockIdx.y * LT - HALO;
+    for (int idx = threadIdx.x; idx < LH * LH; idx += RDG_BLOCK) {
+        const int r = idx / LH, c = idx % LH;
+        const int y = y0 + r, x = x0 + c;
+        float a = 0.f, b = 0.f;
+        if (x >= 0 && x < W && y >= 0 && y < H) { a = pred[plane + (size_t)y * W + x]; b = gt[plane + (size_t)y * W + x]; }
+        halo[0][r][c] = a; halo[1][r][c] = b; halo[2][r][c] = a * a; halo[3][r][c] = b * b; halo[4][r][c] = a * b;
+    }
+    __syncthreads();
+    float o[5];
+    blur_tile<5>(halo, hz, o);
+    const int r = threadIdx.x / LT, c = threadIdx.x % LT;
+    const int y = blockIdx.y * LT + r, x = blockIdx.x * LT + c;
+    float ssim_v = 0.f, l1_v = 0.f;
+    if (x < W && y < H) {
+        const float mu1 = o[0], mu2 = o[1];
+        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+        const float s1 = o[2] - mu1_sq, s2 = o[3] - mu2_sq, s12 = o[4] - mu12;
+        const float C1 = 0.0001f, C2 = 0.0009f;
+        const float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2, B1 = mu1_sq + mu2_sq + C1, B2 = s1 + s2 + C2;
+        const float inv = 1.0f / (B1 * B2);
+        ssim_v = A1 * A2 * inv;
+        // partial derivatives of the map w.r.t. (mu1 | E[x^2] | E[xy]) held independent
+        const float d_s1 = -A1 * A2 * inv / B2;
+        const float d_s12 = 2.f * A1 * inv;
+        const float d_mu = (2.f * mu2 * B1 - A1 * 2.f * mu1) / (B1 * B1) * (A2 / B2) + d_s1 * (-2.f * mu1) + d_s12 * (-mu2);
+        const size_t pix = plane + (size_t)y * W + x;
+        if (map_mu) { map_mu[pix] = d_mu; map_s1[pix] = d_s1; map_s12[pix] = d_s12; }
+        l1_v = fabsf(halo[0][r + HALO][c + HALO] - halo[1][r + HALO][c + HALO]);
+    }
+    ssim_v = warp_sum(ssim_v);
+    l1_v = warp_sum(l1_v);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ssim_v; red[1][threadIdx.x >> 5] = l1_v; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int k = 0; k < RDG_BLOCK / 32; ++k) { a += red[0][k]; b += red[1][k]; }
+        atomicAdd(&sums[0], (double)a);
+        atomicAdd(&sums[1], (double)b);
+    }
+}
+
+__global__ void __launch_bounds__(RDG_BLOCK) ssim_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                             int H, int W, const float* __restrict__ map_mu,
+                                                             const float* __restrict__ map_s1, const float* __restrict__ map_s12,
+                                                             float k_ssim, float k_l1, float* __restrict__ dL_dpred) {
+    __shared__ float halo[3][LH][LH + 1];
+    __shared__ float hz[3][LH][LT];
+    const int ch = blockIdx.z;
+    const size_t plane = (size_t)ch * H * W;
+    const int x0 = blockIdx.x * LT - HALO, y0 = blockIdx.y * LT - HALO;
+    for (int idx = threadIdx.x; idx < LH * LH; idx += RDG_BLOCK) {
+        const int r = idx / LH, c = idx % LH;
+        const int y = y0 + r, x = x0 + c;
+        float a = 0.f, b = 0.f, d = 0.f;
+        if (x >= 0 && x < W && y >= 0 && y < H) {
+            const size_t pix = plane + (size_t)y * W + x;
+            a = map_mu[pix]; b = map_s1[pix]; d = map_s12[pix];
+        }
+        halo[0][r][c] = a; halo[1][r][c] = b; halo[2][r][c] = d;
+    }
+    __syncthreads();
+    float o[3];
+    blur_tile<3>(halo, hz, o);
+    const int r = threadIdx.x / LT, c = threadIdx.x % LT;
+    const int y = blockIdx.y * LT + r, x = blockIdx.x * LT + c;
+    if (x < W && y < H) {
+        const size_t pix = plane + (size_t)y * W + x;
+        const float xv = pred[pix], yv = gt[pix];
+        const float dssim = o[0] + 2.f * xv * o[1] + yv * o[2];
+        const float diff = xv - yv;
+        const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+        dL_dpred[pix] = k_ssim * dssim + k_l1 * sgn;
+    }
+}
+
+__global__ void loss_finalize_kernel(const double* __restrict__ sums, double n, float w_l1, float w_dssim, float* __restrict__ out) {
+    const double ssim = sums[0] / n, l1 = sums[1] / n;
+    out[0] = (float)(w_l1 * l1 + w_dssim * (1.0 - ssim));
+    out[1] = (float)l1;
+    out[2] = (float)ssim;
+}
+
+extern "C" int64_t rdg_l1_dssim_workspace_bytes(int32_t channels, int32_t height, int32_t width) {
+    if (channels <= 0 || height <= 0 || width <= 0) return RDG_E_ARG;
+    return 256 + (int64_t)3 * channels * height * width * (int64_t)sizeof(float);
+}
+
+extern "C" int rdg_l1_dssim(const float* pred, const float* gt, int32_t channels, int32_t height, int32_t width,
+                            float w_l1, float w_dssim, float* out_loss, float* dL_dpred,
+                            void* workspace, int64_t workspace_bytes, void* stream) {
+    RDG_CHECK_ARG(pred && gt && out_loss && workspace, "null argument");
+    RDG_CHECK_ARG(channels > 0 && height > 0 && width > 0, "empty image");
+    if (workspace_bytes < rdg_l1_dssim_workspace_bytes(channels, height, width)) {
+        rdg_set_error("rdg_l1_dssim: workspace too small");
+        return RDG_E_CAPACITY;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    double* sums = (double*)workspace;
+    const size_t plane = (size_t)channels * height * width;
+    float* maps = (float*)((char*)workspace + 256);
+    RDG_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), s));
+    const dim3 grid((width + LT - 1) / LT, (height + LT - 1) / LT, channels);
+    const bool need_grad = dL_dpred != nullptr;
+    ssim_fwd_kernel<<<grid, RDG_BLOCK, 0, s>>>(pred, gt, height, width, need_grad ? maps : nullptr,
+                                              need_grad ? maps + plane : nullptr, need_grad ? maps + 2 * plane : nullptr, sums);
+    RDG_CHECK_LAUNCH();
+    const double n = (double)plane;
+    loss_finalize_kernel<<<1, 1, 0, s>>>(sums, n, w_l1, w_dssim, out_loss);
+    if (need_grad) {
+        ssim_bwd_kernel<<<grid, RDG_BLOCK, 0, s>>>(pred, gt, height, width, maps, maps + plane, maps + 2 * plane,
+                                                  (float)(-(double)w_dssim / n), (float)((double)w_l1 / n), dL_dpred);
+    }
+    RDG_CHECK_LAUNCH();
+    return RDG_OK;
+}
+
+// ------------------------------------------------------------------ Pearson ----
+// stats[b][0..4] = sum p, sum g, sum pp, sum gg, sum pg
+__global__ void __launch_bounds__(RDG_BLOCK) pearson_stats_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                                  int W, const int4* __restrict__ boxes, double* __restrict__ stats) {
+    __shared__ double red[5][RDG_BLOCK / 32];
+    const int4 bx = boxes[blockIdx.y];   // row0, col0, rows, cols
+    const int64_t n = (int64_t)bx.z * bx.w;
+    double s[5] = {0, 0, 0, 0, 0};
+    for (int64_t e = (int64_t)blockIdx.x * RDG_BLOCK + threadIdx.x; e < n; e += (int64_t)gridDim.x * RDG_BLOCK) {
+        const int r = (int)(e / bx.w), c = (int)(e % bx.w);
+        const size_t pix = (size_t)(bx.x + r) * W + bx.y + c;
+        const double p = pred[pix], g = gt[pix];
+        s[0] += p; s[1] += g; s[2] += p * p; s[3] += g * g; s[4] += p * g;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = s[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double t = 0;
+        for (int w = 0; w < RDG_BLOCK / 32; ++w) t += red[threadIdx.x][w];
+        atomicAdd(&stats[blockIdx.y * 8 + threadIdx.x], t);
+    }
+}
+
+__global__ void __launch_bounds__(RDG_BLOCK) pearson_grad_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                                 int W, const int4* __restrict__ boxes, const float* __restrict__ box_weight,
+                                                                 const double* __restrict__ stats, float eps,
+                                                                 float* __restrict__ out_loss, float* __restrict__ dL_dpred) {
+    const int4 bx = boxes[blockIdx.y];
+    const double n = (double)bx.z * (double)bx.w;
+    const double* st = stats + blockIdx.y * 8;
+    const double mp = st[0] / n, mg = st[1] / n;
+    const double varp = fmax((st[2] - n * mp * mp) / (n - 1.0), 0.0), varg = fmax((st[3] - n * mg * mg) / (n - 1.0), 0.0);
+    const double sp = sqrt(varp), sg = sqrt(varg);
+    const double a = sp + (double)eps, b = sg + (double)eps;
+    const double spg = st[4] - n * mp * mg;
+    const double cov = spg / (n * a * b);
+    if (blockIdx.x == 0 && threadIdx.x == 0) out_loss[blockIdx.y] = (float)(1.0 - cov);
+    if (!dL_dpred) return;
+    const double wgt = box_weight ? (double)box_weight[blockIdx.y] : 1.0;
+    const double k1 = 1.0 / (n * a * b);
+    const double k2 = sp > 0.0 ? spg / (n * a * a * b) / ((n - 1.0) * sp) : 0.0;
+    const int64_t cnt = (int64_t)bx.z * bx.w;
+    for (int64_t e = (int64_t)blockIdx.x * RDG_BLOCK + threadIdx.x; e < cnt; e += (int64_t)gridDim.x * RDG_BLOCK) {
+        const int r = (int)(e / bx.w), c = (int)(e % bx.w);
+        const size_t pix = (size_t)(bx.x + r) * W + bx.y + c;
+        const double p = pred[pix], g = gt[pix];
+        const double dcov = (g - mg) * k1 - (p - mp) * k2;
+        atomicAdd(&dL_dpred[pix], (float)(-wgt * dcov));
+    }
+}
+
+extern "C" int rdg_pearson(const float* pred, const float* gt, int32_t height, int32_t width,
+                           const int32_t* boxes, const float* box_weight, int32_t n_boxes, float eps,
+                           float* out_loss, float* dL_dpred, double* stats, void* stream) {
+    RDG_CHECK_ARG(pred && gt && boxes && out_loss && stats, "null argument");
+    RDG_CHECK_ARG(height > 0 && width > 0, "empty image");
+    if (n_boxes <= 0) return RDG_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    RDG_CUDA(cudaMemsetAsync(stats, 0, (size_t)n_boxes * 8 * sizeof(double), s));
+    // whole-image boxes get many CTAs, 128x128 boxes a few
+    const int per_box = n_boxes == 1 ? RDG_SM_COUNT * 2 : 8;
+    const dim3 grid(per_box, n_boxes);
+    pearson_stats_kernel<<<grid, RDG_BLOCK, 0, s>>>(pred, gt, width, (const int4*)boxes, stats);
+    pearson_grad_kernel<<<grid, RDG_BLOCK, 0, s>>>(pred, gt, width, (const int4*)boxes, box_weight, stats, eps, out_loss, dL_dpred);
+    RDG_CHECK_LAUNCH();
+    return RDG_OK;
+}
+
+// --------------------------------------------------------------------- Adam ----
+__global__ void __launch_bounds__(RDG_BLOCK) adam_kernel(float* __restrict__ param, const float* __restrict__ grad,
+                                                         float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                                                         float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale) {
+    for (int64_t i = (int64_t)blockIdx.x * RDG_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * RDG_BLOCK) {
+        const float g = grad[i] * gscale;
+        const float mi = b1 * m[i] + (1.f - b1) * g;
+        const float vi = b2 * v[i] + (1.f - b2) * g * g;
+        m[i] = mi; v[i] = vi;
+        // torch.optim.Adam: denom = sqrt(v)/sqrt(bias2) + eps; step = lr / bias1
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        param[i] -= (lr / bc1) * (mi / denom);
+    }
+}
+
+extern "C" int rdg_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream) {
+    RDG_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "null argument");
+    RDG_CHECK_ARG(step >= 1, "step must be >= 1");
+    if (n <= 0) return RDG_OK;
+    const float bc1 = 1.0f - (float)pow((double)beta1, (double)step);
+    const float bc2 = 1.0f - (float)pow((double)beta2, (double)step);
+    const int64_t want = (n + RDG_BLOCK - 1) / RDG_BLOCK;
+    const int grid = (int)(want < (int64_t)RDG_SM_COUNT * 8 ? want : (int64_t)RDG_SM_COUNT * 8);
+    adam_kernel<<<grid, RDG_BLOCK, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                            bc1, sqrtf(bc2), grad_scale);
+    RDG_CHECK_LAUNCH();
+    return RDG_OK;
+}

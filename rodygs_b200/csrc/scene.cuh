@@ -1,0 +1,192 @@
+// Per-Gaussian parameter fetch shared by preprocess forward and backward:
+// static||dynamic addressing without a concat, activations and the
+// time-conditioned deformation, all in registers.
+//
+// Replaces, per Gaussian:
+//   /root/reference/src/model/rodygs_static.py:82-105   (exp / normalize / sigmoid getters)
+//   /root/reference/src/model/rodygs_dynamic.py:122-138 (c . (B(t) - B(t_i)), * spatial_lr_scale)
+//   /root/reference/src/trainer/rodygs.py:68-113        (static first, dynamic second; delta-q added
+//                                                        to the normalised quaternion, not re-normalised)
+#pragma once
+#include "common.cuh"
+
+struct RdgAct {
+    float x, y, z;     // (deformed) mean
+    float s[3];        // activated scale, before scale_modifier
+    float q[4];        // quaternion as the rasterizer uses it (r,x,y,z)
+    float op;          // opacity in [0,1]
+    float qn[4];       // raw only: normalised raw quaternion
+    float qinv;        // raw only: 1 / max(|raw|, 1e-12)
+    float c[RDG_NUM_BASIS_MAX];  // dynamic only: motion coefficients
+    int ti;            // dynamic only: birth-frame index
+    bool dyn;
+    int64_t local;     // index inside its own set
+};
+
+// Motion-basis difference D[t][k][j] = B(t)[k][j] - table[t][k][j]; `diff` may
+// live in shared memory (staged per block) or be null, in which case it is
+// formed on the fly from global memory.
+__device__ __forceinline__ float rdg_basis_diff(const RdgScene& sc, const float* diff, int ti, int k, int j) {
+    if (diff) return diff[(ti * sc.num_basis + k) * 7 + j];
+    return sc.basis_t[k * 7 + j] - sc.table[((int64_t)ti * sc.num_basis + k) * 7 + j];
+}
+
+template <bool RAW>
+__device__ __forceinline__ void rdg_fetch(const RdgScene& sc, int64_t i, const float* diff, RdgAct& a) {
+    a.dyn = i >= sc.n_static;
+    a.local = a.dyn ? i - sc.n_static : i;
+    const RdgSet& set = a.dyn ? sc.dy : sc.st;
+    const float* px = set.xyz + a.local * 3;
+    const float* ps = set.scaling + a.local * 3;
+    const float* pq = set.rotation + a.local * 4;
+    a.x = px[0]; a.y = px[1]; a.z = px[2];
+    float s0 = ps[0], s1 = ps[1], s2 = ps[2];
+    float q0 = pq[0], q1 = pq[1], q2 = pq[2], q3 = pq[3];
+    float o = set.opacity[a.local];
+    a.ti = 0;
+    if (RAW) {
+        a.s[0] = expf(s0); a.s[1] = expf(s1); a.s[2] = expf(s2);
+        float nrm = sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+        a.qinv = 1.0f / fmaxf(nrm, 1e-12f);
+        a.qn[0] = q0 * a.qinv; a.qn[1] = q1 * a.qinv; a.qn[2] = q2 * a.qinv; a.qn[3] = q3 * a.qinv;
+        a.q[0] = a.qn[0]; a.q[1] = a.qn[1]; a.q[2] = a.qn[2]; a.q[3] = a.qn[3];
+        a.op = 1.0f / (1.0f + expf(-o));
+        if (a.dyn && sc.use_deform) {
+            const float* pc = sc.motion_coeff + a.local * sc.num_basis;
+            a.ti = sc.time_ind[a.local];
+            float d[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < sc.num_basis; ++k) {
+                float ck = pc[k];
+                a.c[k] = ck;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) d[j] += ck * rdg_basis_diff(sc, diff, a.ti, k, j);
+            }
+            a.x += d[0] * sc.spatial_lr_scale;
+            a.y += d[1] * sc.spatial_lr_scale;
+            a.z += d[2] * sc.spatial_lr_scale;
+            a.q[0] += d[3]; a.q[1] += d[4]; a.q[2] += d[5]; a.q[3] += d[6];
+        }
+    } else {
+        a.s[0] = s0; a.s[1] = s1; a.s[2] = s2;
+        a.q[0] = q0; a.q[1] = q1; a.q[2] = q2; a.q[3] = q3;
+        a.qn[0] = q0; a.qn[1] = q1; a.qn[2] = q2; a.qn[3] = q3;
+        a.qinv = 1.0f;
+        a.op = o;
+    }
+}
+
+// Everything downstream of the activated parameters that both passes need.
+struct RdgProj {
+    float tx, ty, tz;          // view-space mean
+    float hx, hy, hw, pw;      // clip space and 1/(w+1e-7)
+    float R[9];                // rotation from the quaternion (row-major)
+    float M[9];                // R * diag(s * scale_modifier)
+    float S[6];                // Sigma: 00 01 02 11 12 22
+    float ctx, cty;            // clamped t.x, t.y used in J
+    bool in_x, in_y;
+    float J00, J02, J11, J12;
+    float T[6];                // J*W: T00 T01 T02 T10 T11 T12
+    float ca, cb, cc;          // 2D covariance after the low-pass
+    float det;
+};
+
+// App. A.2 steps 1-5 in the exact operation order of oracle/splat_oracle.py
+// (the forward translation unit is compiled with -fmad=false).
+__device__ __forceinline__ void rdg_project(const RdgCam& cam, const RdgAct& a, float scale_modifier, RdgProj& p) {
+    const float* V = cam.V;
+    const float* P = cam.P;
+    p.tx = V[0] * a.x + V[1] * a.y + V[2] * a.z + V[3];
+    p.ty = V[4] * a.x + V[5] * a.y + V[6] * a.z + V[7];
+    p.tz = V[8] * a.x + V[9] * a.y + V[10] * a.z + V[11];
+    p.hx = P[0] * p.tx + P[1] * p.ty + P[2] * p.tz + P[3];
+    p.hy = P[4] * p.tx + P[5] * p.ty + P[6] * p.tz + P[7];
+    p.hw = P[12] * p.tx + P[13] * p.ty + P[14] * p.tz + P[15];
+    p.pw = 1.0f / (p.hw + 0.0000001f);
+
+    const float qr = a.q[0], qx = a.q[1], qy = a.q[2], qz = a.q[3];
+    p.R[0] = 1.0f - 2.0f * (qy * qy + qz * qz);
+    p.R[1] = 2.0f * (qx * qy - qr * qz);
+    p.R[2] = 2.0f * (qx * qz + qr * qy);
+    p.R[3] = 2.0f * (qx * qy + qr * qz);
+    p.R[4] = 1.0f - 2.0f * (qx * qx + qz * qz);
+    p.R[5] = 2.0f * (qy * qz - qr * qx);
+    p.R[6] = 2.0f * (qx * qz - qr * qy);
+    p.R[7] = 2.0f * (qy * qz + qr * qx);
+    p.R[8] = 1.0f - 2.0f * (qx * qx + qy * qy);
+    const float s0 = a.s[0] * scale_modifier, s1 = a.s[1] * scale_modifier, s2 = a.s[2] * scale_modifier;
+    float* M = p.M;
+    M[0] = p.R[0] * s0; M[1] = p.R[1] * s1; M[2] = p.R[2] * s2;
+    M[3] = p.R[3] * s0; M[4] = p.R[4] * s1; M[5] = p.R[5] * s2;
+    M[6] = p.R[6] * s0; M[7] = p.R[7] * s1; M[8] = p.R[8] * s2;
+    p.S[0] = M[0] * M[0] + M[1] * M[1] + M[2] * M[2];
+    p.S[1] = M[0] * M[3] + M[1] * M[4] + M[2] * M[5];
+    p.S[2] = M[0] * M[6] + M[1] * M[7] + M[2] * M[8];
+    p.S[3] = M[3] * M[3] + M[4] * M[4] + M[5] * M[5];
+    p.S[4] = M[3] * M[6] + M[4] * M[7] + M[5] * M[8];
+    p.S[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
+
+    const float txtz = p.tx / p.tz;
+    const float tytz = p.ty / p.tz;
+    p.in_x = (txtz >= -cam.limx) && (txtz <= cam.limx);
+    p.in_y = (tytz >= -cam.limy) && (tytz <= cam.limy);
+    p.ctx = fminf(cam.limx, fmaxf(-cam.limx, txtz)) * p.tz;
+    p.cty = fminf(cam.limy, fmaxf(-cam.limy, tytz)) * p.tz;
+    const float tz2 = p.tz * p.tz;
+    p.J00 = cam.fx / p.tz;
+    p.J02 = -(cam.fx * p.ctx) / tz2;
+    p.J11 = cam.fy / p.tz;
+    p.J12 = -(cam.fy * p.cty) / tz2;
+    float* T = p.T;
+    T[0] = p.J00 * V[0] + p.J02 * V[8];
+    T[1] = p.J00 * V[1] + p.J02 * V[9];
+    T[2] = p.J00 * V[2] + p.J02 * V[10];
+    T[3] = p.J11 * V[4] + p.J12 * V[8];
+    T[4] = p.J11 * V[5] + p.J12 * V[9];
+    T[5] = p.J11 * V[6] + p.J12 * V[10];
+    const float* S = p.S;
+    const float U00 = T[0] * S[0] + T[1] * S[1] + T[2] * S[2];
+    const float U01 = T[0] * S[1] + T[1] * S[3] + T[2] * S[4];
+    const float U02 = T[0] * S[2] + T[1] * S[4] + T[2] * S[5];
+    const float U10 = T[3] * S[0] + T[4] * S[1] + T[5] * S[2];
+    const float U11 = T[3] * S[1] + T[4] * S[3] + T[5] * S[4];
+    const float U12 = T[3] * S[2] + T[4] * S[4] + T[5] * S[5];
+    p.ca = U00 * T[0] + U01 * T[1] + U02 * T[2] + RDG_LOWPASS;
+    p.cb = U00 * T[3] + U01 * T[4] + U02 * T[5];
+    p.cc = U10 * T[3] + U11 * T[4] + U12 * T[5] + RDG_LOWPASS;
+    p.det = p.ca * p.cc - p.cb * p.cb;
+}
+
+// SH basis values for a unit direction (sh_utils.py:72-101), b[0..K-1].
+__device__ __forceinline__ void rdg_sh_basis(int deg, float x, float y, float z, float* b) {
+    b[0] = RDG_SH_C0;
+    if (deg > 0) {
+        b[1] = -RDG_SH_C1 * y;
+        b[2] = RDG_SH_C1 * z;
+        b[3] = -RDG_SH_C1 * x;
+        if (deg > 1) {
+            float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            b[4] = RDG_SH_C2_0 * xy;
+            b[5] = RDG_SH_C2_1 * yz;
+            b[6] = RDG_SH_C2_2 * (2.0f * zz - xx - yy);
+            b[7] = RDG_SH_C2_3 * xz;
+            b[8] = RDG_SH_C2_4 * (xx - yy);
+            if (deg > 2) {
+                b[9] = RDG_SH_C3_0 * y * (3.0f * xx - yy);
+                b[10] = RDG_SH_C3_1 * xy * z;
+                b[11] = RDG_SH_C3_2 * y * (4.0f * zz - xx - yy);
+                b[12] = RDG_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                b[13] = RDG_SH_C3_4 * x * (4.0f * zz - xx - yy);
+                b[14] = RDG_SH_C3_5 * z * (xx - yy);
+                b[15] = RDG_SH_C3_6 * x * (xx - 3.0f * yy);
+            }
+        }
+    }
+}
+
+// camera position  -R^T T  from the unpacked view matrix
+__device__ __forceinline__ void rdg_campos(const RdgCam& cam, float* cp) {
+    const float* V = cam.V;
+    cp[0] = -(V[0] * V[3] + V[4] * V[7] + V[8] * V[11]);
+    cp[1] = -(V[1] * V[3] + V[5] * V[7] + V[9] * V[11]);
+    cp[2] = -(V[2] * V[3] + V[6] * V[7] + V[10] * V[11]);
+}

@@ -1,0 +1,337 @@
+"""Host-side driver of one render (forward) and its backward through the C ABI.
+
+Both public entry points sit on top of this module:
+  * rodygs_b200.rasterizer  - the drop-in `GaussianRasterizer` boundary
+    (/root/reference/src/trainer/renderer.py:50-101), activated + concatenated inputs;
+  * rodygs_b200.dynamic     - the fused path on raw parameters of the static and the
+    dynamic model (replaces rodygs.py:68-113 + rodygs_static.py:82-105 +
+    rodygs_dynamic.py:122-138 + the render call).
+
+PyTorch is plumbing here: it owns the device memory and the stream.  All compute
+is in librodygs_b200.so; nothing in this file computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import RdgBins, RdgGeom, RdgImage, RdgScene, RdgSceneGrad, RdgSet, RdgSetGrad, RdgView, check, ptr
+
+TILE = 16
+NACC = 12
+
+
+class Config:
+    """Process-wide knobs.
+
+    sync_free: False (default) keeps the reference's behaviour of one host read of the
+      duplicate count per forward (upstream reads `num_rendered` to size its binning
+      buffers) and transparently re-bins with a larger buffer on overflow.  True never
+      synchronises: the count stays on the device, buffers are sized from the high-water
+      mark times `headroom`, and an overflow is raised at the next call.
+    """
+    sync_free: bool = False
+    headroom: float = 1.25
+    min_capacity: int = 1 << 16
+    debug_keep_unsorted: bool = False   # tests: keep duplicateWithKeys' output
+    debug_activated: bool = False       # tests: dump the activated parameters the kernel used
+
+
+config = Config()
+
+# per-device duplicate-capacity state: {"cap": int, "pending": (pinned tensor, event) | None}
+_capacity: Dict[int, dict] = {}
+
+
+def _cap_state(device: torch.device, n: int) -> dict:
+    st = _capacity.get(device.index)
+    if st is None:
+        st = {"cap": max(config.min_capacity, 4 * n), "pending": None}
+        _capacity[device.index] = st
+    return st
+
+
+def reset_capacity():
+    _capacity.clear()
+
+
+def _check_pending(st: dict):
+    """Look at the duplicate count of an earlier sync-free call (already finished)."""
+    pend = st["pending"]
+    if pend is None:
+        return
+    host, ev, cap_used = pend
+    ev.synchronize()
+    st["pending"] = None
+    d = int(host[0])
+    if d > cap_used:
+        st["cap"] = int(d * config.headroom) + 1
+        raise RuntimeError(
+            f"rodygs_b200: a previous sync-free render produced {d} tile instances but its buffers held "
+            f"{cap_used}; that frame was truncated. Capacity is now {st['cap']}; re-run the step "
+            "(or set rodygs_b200.config.sync_free = False).")
+    if d * config.headroom > st["cap"]:
+        st["cap"] = int(d * config.headroom) + 1
+
+
+@dataclass
+class SetArgs:
+    xyz: torch.Tensor
+    scaling: torch.Tensor
+    rotation: torch.Tensor
+    opacity: torch.Tensor
+    sh_dc: Optional[torch.Tensor]
+    sh_rest: Optional[torch.Tensor]
+    sh_dc_stride: int = 3
+    sh_rest_stride: int = 45
+    sh_rest_offset: int = 0     # float offset of sh_rest inside its tensor (3 for a cat'ed [n,16,3])
+
+    def n(self) -> int:
+        return 0 if self.xyz is None else self.xyz.shape[0]
+
+
+@dataclass
+class SceneArgs:
+    st: Optional[SetArgs]
+    dy: Optional[SetArgs] = None
+    raw: bool = False
+    colors_precomp: Optional[torch.Tensor] = None
+    use_deform: bool = False
+    motion_coeff: Optional[torch.Tensor] = None   # [nd, K]
+    time_ind: Optional[torch.Tensor] = None       # [nd] int32
+    basis_t: Optional[torch.Tensor] = None        # [K,7]
+    table: Optional[torch.Tensor] = None          # [T,K,7]
+    spatial_lr_scale: float = 1.0
+
+    def counts(self):
+        ns = self.st.n() if self.st is not None else 0
+        nd = self.dy.n() if self.dy is not None else 0
+        return ns, nd
+
+
+@dataclass
+class ViewArgs:
+    height: int
+    width: int
+    tanfovx: float
+    tanfovy: float
+    scale_modifier: float
+    sh_degree: int
+    viewmatrix: torch.Tensor   # [4,4] glm storage, contiguous
+    projmatrix: torch.Tensor
+    bg: torch.Tensor
+    enable_cov_grad: bool = True
+    enable_sh_grad: bool = True
+
+
+@dataclass
+class FwdState:
+    """Everything the backward pass needs (kept alive by the autograd ctx)."""
+    scene: SceneArgs
+    view: ViewArgs
+    n: int
+    geom: dict
+    vals_sorted: torch.Tensor
+    ranges: torch.Tensor
+    num_rendered: torch.Tensor
+    final_T: torch.Tensor
+    n_contrib: torch.Tensor
+    d_cap: int
+    extras: dict = field(default_factory=dict)
+
+
+def _set_struct(s: Optional[SetArgs]) -> RdgSet:
+    out = RdgSet()
+    if s is None or s.n() == 0:
+        return out
+    out.xyz = ptr(s.xyz)
+    out.scaling = ptr(s.scaling)
+    out.rotation = ptr(s.rotation)
+    out.opacity = ptr(s.opacity)
+    out.sh_dc = ptr(s.sh_dc)
+    out.sh_rest = None if s.sh_rest is None else s.sh_rest.data_ptr() + 4 * s.sh_rest_offset
+    out.sh_dc_stride = s.sh_dc_stride
+    out.sh_rest_stride = s.sh_rest_stride
+    return out
+
+
+def _scene_struct(sc: SceneArgs) -> RdgScene:
+    ns, nd = sc.counts()
+    out = RdgScene()
+    out.n_static, out.n_dynamic = ns, nd
+    out.st = _set_struct(sc.st)
+    out.dy = _set_struct(sc.dy)
+    out.raw = 1 if sc.raw else 0
+    out.colors_precomp = ptr(sc.colors_precomp)
+    out.use_deform = 1 if (sc.use_deform and nd > 0) else 0
+    if out.use_deform:
+        out.num_basis = sc.motion_coeff.shape[-1]
+        out.num_times = sc.table.shape[0]
+        out.motion_coeff = ptr(sc.motion_coeff)
+        out.time_ind = ptr(sc.time_ind)
+        out.basis_t = ptr(sc.basis_t)
+        out.table = ptr(sc.table)
+    out.spatial_lr_scale = float(sc.spatial_lr_scale)
+    return out
+
+
+def _view_struct(v: ViewArgs) -> RdgView:
+    out = RdgView()
+    out.height, out.width = int(v.height), int(v.width)
+    out.tanfovx, out.tanfovy = float(v.tanfovx), float(v.tanfovy)
+    out.scale_modifier = float(v.scale_modifier)
+    out.sh_degree = int(v.sh_degree)
+    out.enable_cov_grad = 1 if v.enable_cov_grad else 0
+    out.enable_sh_grad = 1 if v.enable_sh_grad else 0
+    out.viewmatrix = ptr(v.viewmatrix)
+    out.projmatrix = ptr(v.projmatrix)
+    out.bg = ptr(v.bg)
+    return out
+
+
+def _geom_struct(g: dict) -> RdgGeom:
+    out = RdgGeom()
+    out.radii = ptr(g["radii"])
+    out.tiles_touched = ptr(g["tiles_touched"])
+    out.p0, out.p1, out.p2 = ptr(g["p0"]), ptr(g["p1"]), ptr(g["p2"])
+    out.clamped = ptr(g["clamped"])
+    out.dbg_activated = ptr(g.get("dbg_activated"))
+    return out
+
+
+def tiles_of(h: int, w: int) -> int:
+    return ((h + TILE - 1) // TILE) * ((w + TILE - 1) // TILE)
+
+
+def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = True):
+    """preprocess -> bin -> blend.  Returns (color, depth, alpha, radii, FwdState)."""
+    lib = _lib.load()
+    ns, nd = scene.counts()
+    n = ns + nd
+    dev = view.viewmatrix.device
+    if dev.type != "cuda":
+        raise RuntimeError("rodygs_b200 runs on CUDA tensors only (no CPU fallback)")
+    stream = _lib.stream_ptr()
+    H, W = int(view.height), int(view.width)
+    f32 = dict(dtype=torch.float32, device=dev)
+    geom = {
+        "radii": torch.empty(n, dtype=torch.int32, device=dev),
+        "tiles_touched": torch.empty(n, dtype=torch.int32, device=dev),
+        "p0": torch.empty(n, 4, **f32), "p1": torch.empty(n, 4, **f32), "p2": torch.empty(n, 2, **f32),
+        "clamped": torch.empty(n, dtype=torch.uint8, device=dev),
+    }
+    if config.debug_activated:
+        geom["dbg_activated"] = torch.zeros(n, 11, **f32)
+    sc_s, vw_s, gm_s = _scene_struct(scene), _view_struct(view), _geom_struct(geom)
+    check(lib.rdg_preprocess_fwd(C.byref(sc_s), C.byref(vw_s), C.byref(gm_s), stream))
+
+    st = _cap_state(dev, n)
+    _check_pending(st)
+    ntiles = tiles_of(H, W)
+    ranges = torch.empty(ntiles, 2, dtype=torch.int32, device=dev)
+    point_offsets = torch.empty(n, dtype=torch.int32, device=dev)
+    num_rendered = torch.empty(2, dtype=torch.int32, device=dev)
+    extras = {}
+    while True:
+        d_cap = int(st["cap"])
+        keys = torch.empty(d_cap, dtype=torch.int64, device=dev)
+        vals = torch.empty(d_cap, dtype=torch.int32, device=dev)
+        ws_bytes = int(lib.rdg_bin_workspace_bytes(n, d_cap, H, W))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        bins = RdgBins()
+        bins.keys_sorted, bins.vals_sorted = ptr(keys), ptr(vals)
+        bins.ranges, bins.point_offsets, bins.num_rendered = ptr(ranges), ptr(point_offsets), ptr(num_rendered)
+        if config.debug_keep_unsorted:
+            extras["keys_unsorted"] = torch.empty(d_cap, dtype=torch.int64, device=dev)
+            extras["vals_unsorted"] = torch.empty(d_cap, dtype=torch.int32, device=dev)
+            bins.keys_unsorted, bins.vals_unsorted = ptr(extras["keys_unsorted"]), ptr(extras["vals_unsorted"])
+        check(lib.rdg_bin(n, C.byref(gm_s), H, W, d_cap, C.byref(bins), ptr(ws), ws_bytes, stream))
+        if config.sync_free:
+            host = torch.empty(2, dtype=torch.int32, pin_memory=True)
+            host.copy_(num_rendered, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            st["pending"] = (host, ev, d_cap)
+            break
+        d = int(num_rendered[0].item())          # the reference's one host read per forward
+        if d <= d_cap:
+            if d * config.headroom > d_cap:
+                st["cap"] = int(d * config.headroom) + 1
+            break
+        st["cap"] = int(d * config.headroom) + 1  # overflow: re-bin with a larger buffer
+
+    color = torch.empty(3, H, W, **f32)
+    depth = torch.empty(1, H, W, **f32)
+    alpha = torch.empty(1, H, W, **f32)
+    final_T = torch.empty(H, W, **f32)
+    n_contrib = torch.empty(H, W, dtype=torch.int32, device=dev)
+    img = RdgImage()
+    img.color, img.depth, img.alpha, img.final_T, img.n_contrib = ptr(color), ptr(depth), ptr(alpha), ptr(final_T), ptr(n_contrib)
+    check(lib.rdg_blend_fwd(n, C.byref(gm_s), C.byref(bins), C.byref(vw_s), C.byref(img), stream))
+
+    extras.update({"keys_sorted": keys, "point_offsets": point_offsets})
+    state = FwdState(scene=scene, view=view, n=n, geom=geom, vals_sorted=vals, ranges=ranges,
+                     num_rendered=num_rendered, final_T=final_T, n_contrib=n_contrib, d_cap=d_cap, extras=extras)
+    return color, depth, alpha, geom["radii"], state
+
+
+@dataclass
+class SetGrads:
+    xyz: Optional[torch.Tensor] = None
+    scaling: Optional[torch.Tensor] = None
+    rotation: Optional[torch.Tensor] = None
+    opacity: Optional[torch.Tensor] = None
+    sh_dc: Optional[torch.Tensor] = None
+    sh_rest: Optional[torch.Tensor] = None
+    sh_rest_offset: int = 0
+
+
+@dataclass
+class SceneGrads:
+    st: SetGrads = field(default_factory=SetGrads)
+    dy: SetGrads = field(default_factory=SetGrads)
+    colors_precomp: Optional[torch.Tensor] = None
+    means2D: Optional[torch.Tensor] = None
+    viewmatrix: Optional[torch.Tensor] = None   # must be zero-initialised
+    motion_coeff: Optional[torch.Tensor] = None
+    table: Optional[torch.Tensor] = None        # must be zero-initialised
+    basis_t: Optional[torch.Tensor] = None      # must be zero-initialised
+
+
+def _setgrad_struct(g: SetGrads) -> RdgSetGrad:
+    out = RdgSetGrad()
+    out.xyz, out.scaling, out.rotation, out.opacity = ptr(g.xyz), ptr(g.scaling), ptr(g.rotation), ptr(g.opacity)
+    out.sh_dc = ptr(g.sh_dc)
+    out.sh_rest = None if g.sh_rest is None else g.sh_rest.data_ptr() + 4 * g.sh_rest_offset
+    return out
+
+
+def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: SceneGrads):
+    """blend backward -> preprocess backward.  Writes into the tensors of `grads`."""
+    lib = _lib.load()
+    dev = state.view.viewmatrix.device
+    stream = _lib.stream_ptr()
+    n = state.n
+    acc = torch.zeros(max(n, 1), NACC, dtype=torch.float32, device=dev)
+    sc_s, vw_s, gm_s = _scene_struct(state.scene), _view_struct(state.view), _geom_struct(state.geom)
+    bins = RdgBins()
+    bins.vals_sorted, bins.ranges, bins.num_rendered = ptr(state.vals_sorted), ptr(state.ranges), ptr(state.num_rendered)
+    img = RdgImage()
+    img.final_T, img.n_contrib = ptr(state.final_T), ptr(state.n_contrib)
+
+    def c(t):
+        return None if t is None else t.contiguous()
+
+    dL_dcolor, dL_ddepth, dL_dalpha = c(dL_dcolor), c(dL_ddepth), c(dL_dalpha)
+    check(lib.rdg_blend_bwd(n, C.byref(gm_s), C.byref(bins), C.byref(vw_s), C.byref(img),
+                            ptr(dL_dcolor), ptr(dL_ddepth), ptr(dL_dalpha), ptr(acc), stream))
+    g = RdgSceneGrad()
+    g.st, g.dy = _setgrad_struct(grads.st), _setgrad_struct(grads.dy)
+    g.colors_precomp, g.means2D, g.viewmatrix = ptr(grads.colors_precomp), ptr(grads.means2D), ptr(grads.viewmatrix)
+    g.motion_coeff, g.table, g.basis_t = ptr(grads.motion_coeff), ptr(grads.table), ptr(grads.basis_t)
+    check(lib.rdg_preprocess_bwd(C.byref(sc_s), C.byref(vw_s), C.byref(gm_s), ptr(acc), C.byref(g), stream))
+    return acc
