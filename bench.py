@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py - train iterations/sec of the dynamic-splatting hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c4_iphone] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one camera-time view per GPU:
+deformation + preprocess + binning + blend forward + (L1 + D-SSIM + Pearson depth + alpha
+term) + full backward to every Gaussian parameter, the motion coefficients, B(t) and the
+motion table (+ the NCCL allreduce of the flat gradient buffer when N > 1).  The optimiser
+is not part of BASELINE.json's metric ("raster fwd+bwd+loss"); `--adam` adds the fused Adam.
+
+`value`  : whole-job iterations/s with that step's inputs (camera, targets) resident in HBM.
+`e2e`    : same metric with the step's inputs (view + projection matrices, B(t), target image
+           and depth) copied from pinned host memory and the loss read back inside the
+           timed region.
+`roofline`: the dominant kernel (largest share of the step, timed with CUDA events on the
+           launching stream inside the timed region) against MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`: the PyTorch-CPU oracle (oracle/) on BASELINE config 1
+           (10K Gaussians, 256x256, 8 frames), scaled to this workload by algorithmic bytes.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train iters/sec (raster fwd+bwd+loss) at 1080p/2M Gaussians; % HBM roofline"
+UNIT = "it/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_oracle_rate(max_frames: int = 8):
+    """PyTorch-CPU oracle on BASELINE config 1; returns (it/s at the sample, description, bytes per iteration)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import deform_oracle as do, loss_oracle as lo, splat_oracle as so
+    from rodygs_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    N, H, W, T, _ = synthetic.CONFIGS["c1_cpu"]
+    sc = synthetic.make_scene(N, H, W, T, seed=0)
+    g = torch.Generator().manual_seed(99)
+    gt = torch.rand(3, H, W, generator=g)
+    gt_d = torch.rand(1, H, W, generator=g)
+    times, stats = [], None
+    for f in range(-1, max_frames):          # frame -1 = warm-up
+        cam = synthetic.make_camera(max(f, 0), 8, H, W, T)
+        t0 = time.perf_counter()
+        st = do.RawGaussians(**{k: x.clone().requires_grad_(True) for k, x in sc["static"].items()})
+        dy = do.RawGaussians(**{k: x.clone().requires_grad_(True) for k, x in sc["dynamic"].items()})
+        coeff = sc["motion_coeff"].clone().requires_grad_(True)
+        table = sc["table"].clone().requires_grad_(True)
+        xyz, op, scl, rot, feat = do.assemble(st, dy, coeff.squeeze(1), table[cam.time_index], table,
+                                              sc["time_ind"].long(), 1.0, True)
+        vm = cam.world_view_transform.t().contiguous().requires_grad_(True)
+        settings = so.Settings(H, W, cam.tanfovx, cam.tanfovy, torch.zeros(3), 1.0,
+                               cam.projection_matrix.t().contiguous(), 3)
+        out = so.rasterize(xyz, torch.zeros(N, 3, requires_grad=True), feat, None, op, scl, rot, vm, settings)
+        loss = lo.photometric(out.color, gt) + 0.05 * lo.pearson_depth(out.depth, gt_d) + 0.01 * (1 - out.alpha).mean()
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if f >= 0:
+            times.append(dt)
+            stats = (N, int((out.radii > 0).sum()), N // 2, int(out.bn.keys.numel()), H * W)
+    rate = len(times) / sum(times)
+    nbytes = synthetic.algorithmic_bytes(*stats)
+    desc = (f"oracle (PyTorch-CPU, fp32) on BASELINE config 1: {N} Gaussians (50% dynamic), {H}x{W}, "
+            f"{len(times)} frames fwd+loss+bwd after 1 warm-up frame; {rate:.3f} it/s at that size")
+    return rate, desc, nbytes
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from rodygs_b200 import synthetic
+    rate, desc, sample_bytes = cpu_oracle_rate(max(2, min(8, args.steps)))
+    N, H, W, T, _ = synthetic.CONFIGS[args.config]
+    full_bytes = synthetic.algorithmic_bytes(N, int(0.9 * N), N // 2, 3 * N, H * W)
+    value = rate * sample_bytes / full_bytes
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config), "note": "CPU arm: bounded sample scaled by algorithmic bytes"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": desc + f"; scaled by algorithmic bytes {sample_bytes / full_bytes:.3e} to {args.config}",
+                         "sample_value": rate},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(cfg):
+    from rodygs_b200 import synthetic
+    N, H, W, T, views = synthetic.CONFIGS[cfg]
+    return f"{cfg}: {N} Gaussians (50% dynamic), {W}x{H}, T={T}, SH degree 3, 1 camera-time view per GPU per step"
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from rodygs_b200 import _lib, engine, synthetic
+    from rodygs_b200.trainer import SplatTrainStep
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    engine.config.sync_free = False   # target generation below sizes the duplicate buffers exactly
+    N, H, W, T, _ = synthetic.CONFIGS[args.config]
+    if args.n_gaussians:
+        N = args.n_gaussians
+    scene_cpu = synthetic.make_scene(N, H, W, T, seed=0)
+    scene = synthetic.to_device(scene_cpu, dev)
+    w_alpha = 0.01 if args.config in ("c4_iphone",) else 0.0
+    step = SplatTrainStep(scene, H, W, sh_degree=3, w_pearson=0.05, w_alpha=w_alpha, device=dev)
+    n_views = max(8, world)
+    my_views = [v for v in range(n_views) if v % world == rank] or [rank % n_views]
+    cams = [synthetic.make_camera(v, n_views, H, W, T) for v in my_views]
+
+    def cam_tensors(cam, device, pin=False):
+        vm = cam.world_view_transform.t().contiguous()
+        pm = cam.projection_matrix.t().contiguous()
+        if pin:
+            return vm.pin_memory(), pm.pin_memory()
+        return vm.to(device), pm.to(device)
+
+    # targets: render of a perturbed copy of the scene, depth min-max normalised
+    targets = []
+    with torch.no_grad():
+        pert = 0.01 * torch.randn(step.p("static.xyz").shape, generator=torch.Generator().manual_seed(1000)).to(dev)
+        step.p("static.xyz").add_(pert)
+        for cam in cams:
+            vm, pm = cam_tensors(cam, dev)
+            step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, step.p("table")[cam.time_index].contiguous(),
+                                  None, None, forward_only=True)
+            color, depth, alpha, _ = step.last_outputs
+            d = depth.clone()
+            d = (d - d.min()) / (d.max() - d.min() + 1e-12)
+            targets.append((color.clone(), d))
+        step.p("static.xyz").sub_(pert)
+    torch.cuda.synchronize()
+    engine.config.sync_free = True    # the timed steps never synchronise the host
+
+    dev_inputs = []
+    host_inputs = []
+    for cam, (gt, gtd) in zip(cams, targets):
+        vm, pm = cam_tensors(cam, dev)
+        bt = step.p("table")[cam.time_index].clone()
+        dev_inputs.append((vm, pm, bt, gt, gtd, cam))
+        hvm, hpm = cam_tensors(cam, None, pin=True)
+        host_inputs.append((hvm, hpm, bt.cpu().pin_memory(), gt.cpu().pin_memory(), gtd.cpu().pin_memory(), cam))
+    # staging buffers for the e2e leg
+    st_vm, st_pm = torch.empty(4, 4, device=dev), torch.empty(4, 4, device=dev)
+    st_bt = torch.empty_like(dev_inputs[0][2])
+    st_gt, st_gtd = torch.empty_like(targets[0][0]), torch.empty_like(targets[0][1])
+    host_loss = torch.empty(8, dtype=torch.float32).pin_memory()
+    h2d_bytes = sum(t.numel() * 4 for t in (st_vm, st_pm, st_bt, st_gt, st_gtd))
+    d2h_bytes = host_loss.numel() * 4
+
+    adam_state = None
+    if args.adam:
+        adam_state = (torch.zeros_like(step.params), torch.zeros_like(step.params))
+    it_count = [0]
+
+    def one_step(k, e2e=False):
+        vm, pm, bt, gt, gtd, cam = (host_inputs if e2e else dev_inputs)[k % len(dev_inputs)]
+        if e2e:
+            st_vm.copy_(vm, non_blocking=True); st_pm.copy_(pm, non_blocking=True); st_bt.copy_(bt, non_blocking=True)
+            st_gt.copy_(gt, non_blocking=True); st_gtd.copy_(gtd, non_blocking=True)
+            vm, pm, bt, gt, gtd = st_vm, st_pm, st_bt, st_gt, st_gtd
+        step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, bt, gt, gtd)
+        if world > 1:
+            step.allreduce_grads(1.0 / world)
+        if adam_state is not None:
+            it_count[0] += 1
+            _lib.check(lib.rdg_adam(step.params.data_ptr(), step.grads.data_ptr(), adam_state[0].data_ptr(),
+                                    adam_state[1].data_ptr(), step.params.numel(), 1.6e-4, 0.9, 0.999, 1e-15,
+                                    it_count[0], 1.0, _lib.stream_ptr()))
+        if e2e:
+            host_loss.copy_(step.loss_parts, non_blocking=True)
+            torch.cuda.current_stream().synchronize()   # the user reads the loss every step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, e2e=False):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for k in range(n_steps):
+            one_step(k, e2e)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for k in range(max(args.warmup, 3)):
+        one_step(k)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = int(lib.rdg_launch_count())
+    step.enable_stage_timing()
+    ms_total = timed(args.steps)
+    launches = int(lib.rdg_launch_count()) - launches0
+    events = step.stage_events
+    step.stage_events = None
+    clocks = sampler.stop() if sampler else None
+
+    # e2e leg (host buffers -> H2D -> step -> D2H loss)
+    for k in range(2):
+        one_step(k, e2e=True)
+    ms_e2e = timed(args.steps, e2e=True)
+
+    # ---- per-stage device times from the events recorded inside the timed region ----
+    stage_ms = {}
+    prev = None
+    for name, ev in events:
+        if name != "start" and prev is not None:
+            stage_ms[name] = stage_ms.get(name, 0.0) + prev.elapsed_time(ev)
+        prev = ev
+    stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
+
+    state = step.last_state
+    D = int(state.num_rendered[0].item())
+    V = int((state.geom["radii"] > 0).sum().item())
+    P = H * W
+    nd = step.nd
+    K = 16
+    stage_bytes = {
+        "preprocess_fwd": 52 * N + (41 + 12 * K) * V + 68 * nd,
+        "bin": 8 * N + 20 * V + 44 * D,
+        "blend_fwd": 44 * D + 28 * P,
+        "loss": 48 * P + (12 * P if step.w[2] else 0),
+        "blend_bwd": 44 * D + 44 * P + 48 * V,
+        "preprocess_bwd": 100 * N + (48 + 24 * K) * V + 132 * nd,
+    }
+    total_bytes = synthetic.algorithmic_bytes(N, V, nd, D, P, K)
+    peak, peak_src = load_peaks()
+    dom = max(stage_ms, key=stage_ms.get) if stage_ms else "blend_bwd"
+    dom_ms = stage_ms.get(dom, float("nan"))
+    achieved = stage_bytes[dom] / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.config, {}).get(dom)
+        except Exception:
+            traffic = None
+
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        value = world * 1000.0 / ms_step
+        e2e_value = world * 1000.0 / (ms_e2e / args.steps)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, desc, sample_bytes = cpu_oracle_rate(8)
+            scaled = rate * sample_bytes / total_bytes
+            cpu = {"value": scaled, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": desc + f"; scaled by algorithmic bytes ({sample_bytes / total_bytes:.3e}) to this workload",
+                   "sample_value": rate}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.config), "n_gaussians": N, "visible": V, "duplicates": D,
+                       "pixels": P, "views_per_step": world, "l2": "inputs larger than L2 (params+SH 472 MB, sort buffers)",
+                       "optimizer": "fused Adam in the timed region" if args.adam else "excluded (metric = raster fwd+bwd+loss)",
+                       "sync_free": True, "parallelism": f"dp{world} (view-sharded, allreduce of flat grads)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel_ms": dom_ms, "algorithmic_bytes": stage_bytes[dom]},
+            "step_roofline": {"algorithmic_bytes": total_bytes, "achieved": total_bytes / (ms_step * 1e-3) / 1e9,
+                              "frac": total_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                              "note": "whole step (all kernels + launch gaps) against the HBM peak"},
+            "stage_ms": stage_ms,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c4_iphone")
+    ap.add_argument("--n-gaussians", type=int, default=0)
+    ap.add_argument("--adam", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU oracle arm)")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

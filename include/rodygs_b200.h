@@ -139,6 +139,8 @@ typedef struct RdgSceneGrad {
 
 int rdg_abi_version(void);
 const char* rdg_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
+uint64_t rdg_launch_count(void);
 
 /* ---- forward ------------------------------------------------------------ */
 
@@ -189,6 +191,11 @@ int rdg_l1_dssim(const float* pred, const float* gt, int32_t channels, int32_t h
 int rdg_pearson(const float* pred, const float* gt, int32_t height, int32_t width,
                 const int32_t* boxes, const float* box_weight, int32_t n_boxes, float eps,
                 float* out_loss, float* dL_dpred, double* stats, void* stream);
+
+/* w * mean(1 - alpha) over n pixels: out_loss[0] += that value, dL_dalpha[i] = -w / n.
+ * Benchmark-only regulariser of BASELINE.json config 4 ("depth+alpha regularisers");
+ * the reference itself has no alpha consumer. */
+int rdg_alpha_reg(const float* alpha, int64_t n, float weight, float* out_loss, float* dL_dalpha, void* stream);
 
 /* ---- optimiser (next row) ------------------------------------ */
 

@@ -63,6 +63,8 @@ class RdgSceneGrad(C.Structure):
 SYMBOLS = {
     "rdg_abi_version": (C.c_int, []),
     "rdg_last_error": (C.c_char_p, []),
+    "rdg_launch_count": (C.c_uint64, []),
+    "rdg_alpha_reg": (C.c_int, [c_ptr, C.c_int64, C.c_float, c_ptr, c_ptr, c_ptr]),
     "rdg_preprocess_fwd": (C.c_int, [C.POINTER(RdgScene), C.POINTER(RdgView), C.POINTER(RdgGeom), c_ptr]),
     "rdg_bin_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "rdg_bin": (C.c_int, [C.c_int64, C.POINTER(RdgGeom), C.c_int32, C.c_int32, C.c_int64, C.POINTER(RdgBins),

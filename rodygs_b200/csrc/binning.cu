@@ -134,6 +134,7 @@ static int scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* sums
     scan_sums_kernel<<<1, 1024, 0, s>>>(sums_ws, nb, total_out, cap);
     scan_apply_kernel<INCLUSIVE><<<nb, RDG_BLOCK, 0, s>>>(in, out, n, sums_ws);
     RDG_CHECK_LAUNCH();
+    rdg_count_launches(3);
     return RDG_OK;
 }
 
@@ -331,7 +332,7 @@ extern "C" int rdg_bin(int64_t n, const RdgGeom* geom, int32_t height, int32_t w
                        const RdgBins* bins, void* workspace, int64_t workspace_bytes, void* stream) {
     RDG_CHECK_ARG(geom && bins && workspace, "null argument");
     RDG_CHECK_ARG(n >= 0 && d_cap > 0 && d_cap < (int64_t)0xffffffffLL, "bad sizes");
-    RDG_CHECK_ARG(bins->keys_sorted && bins->vals_sorted && bins->ranges && bins->point_offsets && bins->num_rendered,
+    RDG_CHECK_ARG(bins->keys_sorted && bins->vals_sorted && bins->ranges && bins->num_rendered && (n == 0 || bins->point_offsets),
                   "null bin buffer");
     const BinLayout L = bin_layout(n, d_cap);
     if (workspace_bytes < L.total) {
@@ -368,6 +369,7 @@ extern "C" int rdg_bin(int64_t n, const RdgGeom* geom, int32_t height, int32_t w
                                                    (const float4*)geom->p0, (const float2*)geom->p2, gx, gy,
                                                    k_src, v_src, (uint32_t)d_cap);
         RDG_CHECK_LAUNCH();
+        rdg_count_launches(1);
     }
     uint32_t* hist = (uint32_t*)(ws + L.hist);
     uint32_t* hist_sums = (uint32_t*)(ws + L.hist_sums);
@@ -382,6 +384,7 @@ extern "C" int rdg_bin(int64_t n, const RdgGeom* geom, int32_t height, int32_t w
         radix_scatter_kernel<<<L.nblk, RDG_BLOCK, 0, s>>>(k_src, v_src, k_dst, v_dst, bins->num_rendered, (uint32_t)d_cap,
                                                         shift, bits, L.nblk, hist);
         RDG_CHECK_LAUNCH();
+        rdg_count_launches(2);
         k_src = k_dst;
         v_src = v_dst;
     }
@@ -389,6 +392,7 @@ extern "C" int rdg_bin(int64_t n, const RdgGeom* geom, int32_t height, int32_t w
         const int grid = (int)(L.nblk * (SORT_TILE / RDG_BLOCK) < RDG_SM_COUNT * 8 ? L.nblk * (SORT_TILE / RDG_BLOCK) : RDG_SM_COUNT * 8);
         tile_ranges_kernel<<<grid, RDG_BLOCK, 0, s>>>(kx, bins->num_rendered, (uint32_t)d_cap, (uint2*)bins->ranges);
         RDG_CHECK_LAUNCH();
+        rdg_count_launches(1);
     }
     return RDG_OK;
 }

@@ -265,6 +265,7 @@ extern "C" int rdg_blend_fwd(int64_t n, const RdgGeom* geom, const RdgBins* bins
         (const uint2*)bins->ranges, bins->vals_sorted, (const float4*)geom->p0, (const float4*)geom->p1,
         (const float2*)geom->p2, view->bg, W, H, gx, out->color, out->depth, out->alpha, out->final_T, out->n_contrib);
     RDG_CHECK_LAUNCH();
+    rdg_count_launches(1);
     return RDG_OK;
 }
 
@@ -280,5 +281,6 @@ extern "C" int rdg_blend_bwd(int64_t n, const RdgGeom* geom, const RdgBins* bins
         (const uint2*)bins->ranges, bins->vals_sorted, (const float4*)geom->p0, (const float4*)geom->p1,
         (const float2*)geom->p2, view->bg, W, H, gx, fwd->final_T, fwd->n_contrib, dL_dcolor, dL_ddepth, dL_dalpha, acc);
     RDG_CHECK_LAUNCH();
+    rdg_count_launches(1);
     return RDG_OK;
 }

@@ -9,6 +9,7 @@
 #define RDG_SM_COUNT 148   // B200: 2 dies x 74 SMs; persistent grids are sized in multiples of this
 
 void rdg_set_error(const char* fmt, ...);
+void rdg_count_launches(int n);
 
 #define RDG_CHECK_ARG(cond, msg)                                   \
     do {                                                           \

@@ -168,6 +168,7 @@ extern "C" int rdg_l1_dssim(const float* pred, const float* gt, int32_t channels
                                                   (float)(-(double)w_dssim / n), (float)((double)w_l1 / n), dL_dpred);
     }
     RDG_CHECK_LAUNCH();
+    rdg_count_launches(need_grad ? 3 : 2);
     return RDG_OK;
 }
 
@@ -241,6 +242,37 @@ extern "C" int rdg_pearson(const float* pred, const float* gt, int32_t height, i
     pearson_stats_kernel<<<grid, RDG_BLOCK, 0, s>>>(pred, gt, width, (const int4*)boxes, stats);
     pearson_grad_kernel<<<grid, RDG_BLOCK, 0, s>>>(pred, gt, width, (const int4*)boxes, box_weight, stats, eps, out_loss, dL_dpred);
     RDG_CHECK_LAUNCH();
+    rdg_count_launches(2);
+    return RDG_OK;
+}
+
+// ------------------------------------------------------------ alpha regulariser ----
+__global__ void __launch_bounds__(RDG_BLOCK) alpha_reg_kernel(const float* __restrict__ alpha, int64_t n, float w_over_n,
+                                                              float* __restrict__ out_loss, float* __restrict__ dL_dalpha) {
+    __shared__ float red[RDG_BLOCK / 32];
+    float s = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * RDG_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * RDG_BLOCK) {
+        s += 1.0f - alpha[i];
+        if (dL_dalpha) dL_dalpha[i] = -w_over_n;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int k = 0; k < RDG_BLOCK / 32; ++k) t += red[k];
+        atomicAdd(out_loss, t * w_over_n);
+    }
+}
+
+extern "C" int rdg_alpha_reg(const float* alpha, int64_t n, float weight, float* out_loss, float* dL_dalpha, void* stream) {
+    RDG_CHECK_ARG(alpha && out_loss, "null argument");
+    if (n <= 0) return RDG_OK;
+    const int64_t want = (n + RDG_BLOCK - 1) / RDG_BLOCK;
+    const int grid = (int)(want < (int64_t)RDG_SM_COUNT * 4 ? want : (int64_t)RDG_SM_COUNT * 4);
+    alpha_reg_kernel<<<grid, RDG_BLOCK, 0, (cudaStream_t)stream>>>(alpha, n, weight / (float)n, out_loss, dL_dalpha);
+    RDG_CHECK_LAUNCH();
+    rdg_count_launches(1);
     return RDG_OK;
 }
 
@@ -271,5 +303,6 @@ extern "C" int rdg_adam(float* param, const float* grad, float* exp_avg, float* 
     adam_kernel<<<grid, RDG_BLOCK, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                             bc1, sqrtf(bc2), grad_scale);
     RDG_CHECK_LAUNCH();
+    rdg_count_launches(1);
     return RDG_OK;
 }

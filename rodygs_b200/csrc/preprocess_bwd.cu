@@ -419,5 +419,6 @@ extern "C" int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, co
         preprocess_bwd_kernel<false><<<grid, RDG_BLOCK, smem, s>>>(p);
     }
     RDG_CHECK_LAUNCH();
+    rdg_count_launches(1);
     return RDG_OK;
 }

@@ -169,9 +169,9 @@ extern "C" int rdg_preprocess_fwd(const RdgScene* scene, const RdgView* view, co
     RDG_CHECK_ARG(view->sh_degree >= 0 && view->sh_degree <= 3, "sh_degree must be 0..3");
     RDG_CHECK_ARG(view->width > 0 && view->height > 0, "empty image");
     RDG_CHECK_ARG(view->viewmatrix && view->projmatrix, "null camera matrix");
+    if (N == 0) return RDG_OK;
     RDG_CHECK_ARG(geom->radii && geom->tiles_touched && geom->p0 && geom->p1 && geom->p2 && geom->clamped,
                   "null geometry buffer");
-    if (N == 0) return RDG_OK;
     RDG_CHECK_ARG(scene->n_static == 0 || (scene->st.xyz && scene->st.scaling && scene->st.rotation && scene->st.opacity),
                   "null static parameter");
     RDG_CHECK_ARG(scene->n_dynamic == 0 || (scene->dy.xyz && scene->dy.scaling && scene->dy.rotation && scene->dy.opacity),
@@ -206,5 +206,6 @@ extern "C" int rdg_preprocess_fwd(const RdgScene* scene, const RdgView* view, co
         preprocess_fwd_kernel<false><<<grid, RDG_BLOCK, smem, s>>>(p);
     }
     RDG_CHECK_LAUNCH();
+    rdg_count_launches(1);
     return RDG_OK;
 }

@@ -207,7 +207,7 @@ def tiles_of(h: int, w: int) -> int:
     return ((h + TILE - 1) // TILE) * ((w + TILE - 1) // TILE)
 
 
-def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = True):
+def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = True, stage_hook=None):
     """preprocess -> bin -> blend.  Returns (color, depth, alpha, radii, FwdState)."""
     lib = _lib.load()
     ns, nd = scene.counts()
@@ -228,6 +228,8 @@ def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = T
         geom["dbg_activated"] = torch.zeros(n, 11, **f32)
     sc_s, vw_s, gm_s = _scene_struct(scene), _view_struct(view), _geom_struct(geom)
     check(lib.rdg_preprocess_fwd(C.byref(sc_s), C.byref(vw_s), C.byref(gm_s), stream))
+    if stage_hook:
+        stage_hook("preprocess_fwd")
 
     st = _cap_state(dev, n)
     _check_pending(st)
@@ -264,6 +266,8 @@ def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = T
             break
         st["cap"] = int(d * config.headroom) + 1  # overflow: re-bin with a larger buffer
 
+    if stage_hook:
+        stage_hook("bin")
     color = torch.empty(3, H, W, **f32)
     depth = torch.empty(1, H, W, **f32)
     alpha = torch.empty(1, H, W, **f32)
@@ -272,6 +276,8 @@ def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = T
     img = RdgImage()
     img.color, img.depth, img.alpha, img.final_T, img.n_contrib = ptr(color), ptr(depth), ptr(alpha), ptr(final_T), ptr(n_contrib)
     check(lib.rdg_blend_fwd(n, C.byref(gm_s), C.byref(bins), C.byref(vw_s), C.byref(img), stream))
+    if stage_hook:
+        stage_hook("blend_fwd")
 
     extras.update({"keys_sorted": keys, "point_offsets": point_offsets})
     state = FwdState(scene=scene, view=view, n=n, geom=geom, vals_sorted=vals, ranges=ranges,
@@ -310,7 +316,7 @@ def _setgrad_struct(g: SetGrads) -> RdgSetGrad:
     return out
 
 
-def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: SceneGrads):
+def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: SceneGrads, stage_hook=None):
     """blend backward -> preprocess backward.  Writes into the tensors of `grads`."""
     lib = _lib.load()
     dev = state.view.viewmatrix.device
@@ -329,9 +335,13 @@ def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: Sce
     dL_dcolor, dL_ddepth, dL_dalpha = c(dL_dcolor), c(dL_ddepth), c(dL_dalpha)
     check(lib.rdg_blend_bwd(n, C.byref(gm_s), C.byref(bins), C.byref(vw_s), C.byref(img),
                             ptr(dL_dcolor), ptr(dL_ddepth), ptr(dL_dalpha), ptr(acc), stream))
+    if stage_hook:
+        stage_hook("blend_bwd")
     g = RdgSceneGrad()
     g.st, g.dy = _setgrad_struct(grads.st), _setgrad_struct(grads.dy)
     g.colors_precomp, g.means2D, g.viewmatrix = ptr(grads.colors_precomp), ptr(grads.means2D), ptr(grads.viewmatrix)
     g.motion_coeff, g.table, g.basis_t = ptr(grads.motion_coeff), ptr(grads.table), ptr(grads.basis_t)
     check(lib.rdg_preprocess_bwd(C.byref(sc_s), C.byref(vw_s), C.byref(gm_s), ptr(acc), C.byref(g), stream))
+    if stage_hook:
+        stage_hook("preprocess_bwd")
     return acc

@@ -1,0 +1,213 @@
+"""Engine-level training step on flat parameter / gradient buffers: the per-iteration
+hot loop of /root/reference/src/trainer/rodygs.py:198-310 (get_GS_properties -> render
+-> MultiLoss -> loss.backward) as ONE explicit sequence of C-ABI calls - no autograd
+graph, no concat, no host synchronisation, gradients written straight into one flat
+fp32 buffer that the data-parallel allreduce consumes.
+
+Multi-GPU: one process per GPU, every rank holds a full replica of the Gaussians and
+renders its own camera-time view(s); the only exchange step is the sum of the flat
+gradient buffer (`torch.distributed.all_reduce`, NCCL over NVLink on the GPU box,
+gloo in the CPU tests).  Pose gradients and the means2D sink stay rank-local.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib, engine
+from ._lib import check, ptr
+from .engine import SceneArgs, SceneGrads, SetArgs, SetGrads, ViewArgs
+
+PARAM_ORDER = ("xyz", "scaling", "rotation", "opacity", "features_dc", "features_rest")
+
+
+def flat_layout(n_static: int, n_dynamic: int, num_basis: int, num_times: int) -> Tuple[Dict[str, Tuple[int, Tuple[int, ...]]], int]:
+    """name -> (float offset, shape) of every trainable tensor inside the flat buffer.
+    Offsets are multiples of 64 floats (256 B) so that every slice is vector-aligned."""
+    shapes = {}
+    for tag, n in (("static", n_static), ("dynamic", n_dynamic)):
+        shapes[f"{tag}.xyz"] = (n, 3)
+        shapes[f"{tag}.scaling"] = (n, 3)
+        shapes[f"{tag}.rotation"] = (n, 4)
+        shapes[f"{tag}.opacity"] = (n, 1)
+        shapes[f"{tag}.features_dc"] = (n, 1, 3)
+        shapes[f"{tag}.features_rest"] = (n, 15, 3)
+    shapes["motion_coeff"] = (n_dynamic, 1, num_basis)
+    shapes["table"] = (num_times, num_basis, 7)
+    shapes["basis_t"] = (num_basis, 7)
+    layout, off = {}, 0
+    for name, shp in shapes.items():
+        numel = 1
+        for s in shp:
+            numel *= s
+        layout[name] = (off, shp)
+        off += (numel + 63) // 64 * 64
+    return layout, off
+
+
+def shard_views(n_views: int, world_size: int, rank: int) -> List[int]:
+    """Round-robin split of a step's camera-time views over the ranks."""
+    return [v for v in range(n_views) if v % world_size == rank]
+
+
+class SplatTrainStep:
+    """Holds the flat parameter and gradient buffers of a static + dynamic model and runs
+    forward + losses + backward for one view.
+
+    loss = w_l1 * L1 + w_dssim * (1 - SSIM)                 (train_kubric_mrig.yaml:135-144)
+         + w_pearson * (1 - Pearson(depth, gt_depth))       (:145-150, global)
+         + w_alpha * mean(1 - alpha)                        (benchmark-only term)
+    """
+
+    def __init__(self, scene: Dict, height: int, width: int, sh_degree: int = 3, w_l1: float = 0.8,
+                 w_dssim: float = 0.2, w_pearson: float = 0.05, w_alpha: float = 0.0, device="cuda",
+                 process_group=None):
+        self.dev = torch.device(device)
+        self.H, self.W, self.sh_degree = int(height), int(width), int(sh_degree)
+        self.w = (float(w_l1), float(w_dssim), float(w_pearson), float(w_alpha))
+        self.pg = process_group
+        ns, nd = scene["static"]["xyz"].shape[0], scene["dynamic"]["xyz"].shape[0]
+        self.ns, self.nd = ns, nd
+        self.num_basis = scene["motion_coeff"].shape[-1]
+        self.T = scene["table"].shape[0]
+        self.layout, total = flat_layout(ns, nd, self.num_basis, self.T)
+        self.params = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.grads = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        for tag in ("static", "dynamic"):
+            for k in PARAM_ORDER:
+                self.p(f"{tag}.{k}").copy_(scene[tag][k])
+        self.p("motion_coeff").copy_(scene["motion_coeff"])
+        self.p("table").copy_(scene["table"])
+        self.time_ind = scene["time_ind"].to(self.dev, torch.int32).contiguous()
+        self.spatial_lr_scale = float(scene["spatial_lr_scale"])
+        self.bg = torch.zeros(3, dtype=torch.float32, device=self.dev)          # rodygs.py:267
+        n = ns + nd
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.means2D_grad = torch.zeros(n, 3, **f32)
+        self.view_grad = torch.zeros(4, 4, **f32)
+        self.loss_parts = torch.zeros(8, **f32)   # [0:3] photometric (loss, l1, ssim), [3] pearson, [4] alpha term
+        self.dL_dcolor = torch.empty(3, self.H, self.W, **f32)
+        self.dL_ddepth = torch.zeros(1, self.H, self.W, **f32)
+        self.dL_dalpha = torch.zeros(1, self.H, self.W, **f32)
+        lib = _lib.load()
+        self._ws_bytes = int(lib.rdg_l1_dssim_workspace_bytes(3, self.H, self.W))
+        self._loss_ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.dev)
+        self._pearson_box = torch.tensor([[0, 0, self.H, self.W]], dtype=torch.int32, device=self.dev)
+        self._pearson_w = torch.tensor([self.w[2]], **f32)
+        self._pearson_stats = torch.zeros(8, dtype=torch.float64, device=self.dev)
+        self._pearson_out = torch.zeros(1, **f32)
+        self.last_state: Optional[engine.FwdState] = None
+        self.stage_events = None   # set by enable_stage_timing()
+
+    # -- views into the flat buffers --------------------------------------------------------
+    def _slice(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        off, shp = self.layout[name]
+        numel = 1
+        for s in shp:
+            numel *= s
+        return buf[off:off + numel].view(shp)
+
+    def p(self, name: str) -> torch.Tensor:
+        return self._slice(self.params, name)
+
+    def g(self, name: str) -> torch.Tensor:
+        return self._slice(self.grads, name)
+
+    def _set(self, tag: str) -> Optional[SetArgs]:
+        if (self.ns if tag == "static" else self.nd) == 0:
+            return None
+        return SetArgs(xyz=self.p(f"{tag}.xyz"), scaling=self.p(f"{tag}.scaling"), rotation=self.p(f"{tag}.rotation"),
+                       opacity=self.p(f"{tag}.opacity"), sh_dc=self.p(f"{tag}.features_dc"),
+                       sh_rest=self.p(f"{tag}.features_rest"), sh_dc_stride=3, sh_rest_stride=45)
+
+    def _setgrad(self, tag: str) -> SetGrads:
+        if (self.ns if tag == "static" else self.nd) == 0:
+            return SetGrads()
+        return SetGrads(xyz=self.g(f"{tag}.xyz"), scaling=self.g(f"{tag}.scaling"), rotation=self.g(f"{tag}.rotation"),
+                        opacity=self.g(f"{tag}.opacity"), sh_dc=self.g(f"{tag}.features_dc"),
+                        sh_rest=self.g(f"{tag}.features_rest"))
+
+    # -- timing hooks --------------------------------------------------------------------------
+    def enable_stage_timing(self):
+        self.stage_events = []
+
+    def _mark(self, name: str):
+        if self.stage_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.stage_events.append((name, ev))
+
+    # -- one view --------------------------------------------------------------------------------
+    def forward_backward(self, viewmatrix: torch.Tensor, projmatrix: torch.Tensor, tanfovx: float, tanfovy: float,
+                         basis_t: torch.Tensor, gt_image: torch.Tensor, gt_depth: Optional[torch.Tensor],
+                         accumulate: bool = False, forward_only: bool = False):
+        """viewmatrix / projmatrix in glm storage (V^T, P^T).  Gradients land in self.grads
+        (overwritten unless accumulate=True, in which case a second flat buffer is summed in).
+        Returns self.loss_parts (device tensor; no host sync)."""
+        lib = _lib.load()
+        stream = _lib.stream_ptr()
+        deform = self.nd > 0
+        scene = SceneArgs(st=self._set("static"), dy=self._set("dynamic"), raw=True, use_deform=deform,
+                          motion_coeff=self.p("motion_coeff").view(self.nd, self.num_basis) if deform else None,
+                          time_ind=self.time_ind if deform else None, basis_t=basis_t if deform else None,
+                          table=self.p("table") if deform else None, spatial_lr_scale=self.spatial_lr_scale)
+        view = ViewArgs(height=self.H, width=self.W, tanfovx=tanfovx, tanfovy=tanfovy, scale_modifier=1.0,
+                        sh_degree=self.sh_degree, viewmatrix=viewmatrix, projmatrix=projmatrix, bg=self.bg)
+        self._mark("start")
+        color, depth, alpha, radii, state = engine.render_forward(scene, view, stage_hook=self._mark)
+        self.last_state = state
+        self.last_outputs = (color, depth, alpha, radii)
+        if forward_only:
+            return None
+        # ---- losses + their gradients w.r.t. the rendered maps (fused kernels) ----
+        w_l1, w_ds, w_p, w_a = self.w
+        self.loss_parts.zero_()
+        check(lib.rdg_l1_dssim(ptr(color), ptr(gt_image), 3, self.H, self.W, w_l1, w_ds, ptr(self.loss_parts),
+                               ptr(self.dL_dcolor), ptr(self._loss_ws), self._ws_bytes, stream))
+        use_depth = w_p != 0.0 and gt_depth is not None
+        if use_depth:
+            self.dL_ddepth.zero_()
+            check(lib.rdg_pearson(ptr(depth), ptr(gt_depth), self.H, self.W, ptr(self._pearson_box), ptr(self._pearson_w), 1,
+                                  1e-6, self.loss_parts[3:4].data_ptr(), ptr(self.dL_ddepth), ptr(self._pearson_stats), stream))
+        use_alpha = w_a != 0.0
+        if use_alpha:
+            check(lib.rdg_alpha_reg(ptr(alpha), self.H * self.W, w_a, self.loss_parts[4:5].data_ptr(), ptr(self.dL_dalpha), stream))
+        self._mark("loss")
+        # ---- backward ----
+        target = self.grads
+        if accumulate:
+            if not hasattr(self, "_grads_tmp"):
+                self._grads_tmp = torch.zeros_like(self.grads)
+            target = self._grads_tmp
+        saved = self.grads
+        self.grads = target
+        try:
+            self.view_grad.zero_()
+            self.g("table").zero_()
+            self.g("basis_t").zero_()
+            grads = SceneGrads(st=self._setgrad("static"), dy=self._setgrad("dynamic"), means2D=self.means2D_grad,
+                               viewmatrix=self.view_grad,
+                               motion_coeff=self.g("motion_coeff").view(self.nd, self.num_basis) if deform else None,
+                               table=self.g("table") if deform else None, basis_t=self.g("basis_t") if deform else None)
+            engine.render_backward(state, self.dL_dcolor, self.dL_ddepth if use_depth else None,
+                                   self.dL_dalpha if use_alpha else None, grads, stage_hook=self._mark)
+        finally:
+            self.grads = saved
+        if accumulate:
+            self.grads.add_(target)
+        return self.loss_parts
+
+    def allreduce_grads(self, scale: Optional[float] = None):
+        """Sum (and optionally scale) the flat gradient buffer over the data-parallel group."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.pg)
+        if scale is not None and scale != 1.0:
+            self.grads.mul_(scale)
+
+    def total_loss(self) -> torch.Tensor:
+        """photometric + w_p * pearson + alpha term (device scalar)."""
+        lp = self.loss_parts
+        return lp[0] + self.w[2] * lp[3] + lp[4]
