@@ -3,29 +3,34 @@
 // App. A.4-A.6 == oracle/splat_oracle.py::blend (+ autograd).
 //
 // B200 mapping
-//  * one CTA per 16x16 tile, 8 warps; warp w owns an 8x4 pixel sub-tile so that a
-//    Gaussian's footprint can be rejected per warp with one broadcast LDS.128 and four
-//    compares (exact alpha >= 1/255 ellipse bound, conservative margin) before any
-//    FP32 / MUFU work is spent;
+//  * one CTA per 16x16 tile, 8 warps; warp w owns an 8x4 pixel sub-tile.
 //  * per-tile batches of 256 Gaussians are staged in shared memory as three packed
-//    records (16 + 16 + 8 bytes) + the bounding box;
-//  * backward: per-Gaussian gradients are reduced across the warp with shuffles only
-//    when some lane contributed, combined across the 8 warps in shared memory, and
+//    records (16 + 16 + 8 bytes).  The staging thread also computes the exact
+//    alpha >= 1/255 ellipse bound of its Gaussian and turns it into an 8-bit mask of the
+//    sub-tiles it can touch; each warp then compacts the batch into its own list with
+//    ballot/popc, so the inner loop only ever visits Gaussians that can contribute to this
+//    warp (28 % of the (warp, Gaussian) pairs at the bench config) - no per-iteration
+//    cull test on the ALU pipe, which was the limiter of the first version (ncu r01).
+//  * backward: the ten per-Gaussian partial gradients are reduced across the warp with a
+//    12-shuffle reduce-scatter butterfly (5+3+2+1+1) instead of 10 x 5 butterflies; the
+//    ten lanes that end up owning a total add it to the CTA's shared accumulators, which
 //    leave the CTA as three 16-byte vector atomics (red.global.add.v4.f32, sm_90+) per
 //    (Gaussian, tile) instead of upstream's ten scalar atomics per (Gaussian, pixel).
-// Bound: FP32 pipe + MUFU (ex2) + shared-memory broadcast; charged against the HBM
-// roofline as north_star asks (algorithmic bytes: 48 B per duplicate + 28 B per pixel
-// forward; 48 B per duplicate + 44 B per pixel backward).
+// Bound: FP32/ALU issue + MUFU (ex2) + shuffle crossbar; charged against the HBM
+// roofline as north_star asks (algorithmic bytes: 44 B per duplicate + 28 B per pixel
+// forward; 44 B per duplicate + 44 B per pixel + 48 B per visible Gaussian backward).
 #include "common.cuh"
 
 #define BATCH 256
+#define NWARP (BATCH / 32)
 
 struct __align__(16) Staged {
-    float4 a[BATCH];    // px, py, A, B
-    float4 b[BATCH];    // C, opacity, r, g
-    float2 c[BATCH];    // b, depth
-    float4 bb[BATCH];   // xmin, xmax, ymin, ymax of the alpha >= 1/255 ellipse
+    float4 a[BATCH];            // px, py, A, B
+    float4 b[BATCH];            // C, opacity, r, g
+    float2 c[BATCH];            // b, depth
     uint32_t id[BATCH];
+    uint8_t wm[BATCH];          // bit w: may touch warp w's 8x4 sub-tile
+    uint8_t list[NWARP][BATCH]; // per-warp compacted batch slots, in list order
 };
 
 // alpha = min(0.99, o * exp(power)); identical instruction sequence in both passes so
@@ -39,17 +44,42 @@ __device__ __forceinline__ bool rdg_alpha(float dx, float dy, float A, float B, 
     return alpha >= RDG_ALPHA_MIN;
 }
 
-__device__ __forceinline__ float4 rdg_bbox(float4 a, float4 b) {
+// 8-bit mask of the 8x4 sub-tiles (bit = sx + 2*sy) that the alpha >= 1/255 ellipse of
+// this Gaussian can reach; conservative (0.1 % + 0.01 px margins), exact rule stays per pixel.
+__device__ __forceinline__ uint32_t rdg_warp_mask(float4 a, float4 b, float tile_x0, float tile_y0) {
     const float A = a.z, B = a.w, C = b.x, o = b.y;
-    const float huge = 3.0e38f;
-    if (!(o >= RDG_ALPHA_MIN)) return make_float4(huge, -huge, huge, -huge);  // can never reach 1/255
+    if (!(o >= RDG_ALPHA_MIN)) return 0u;   // o * exp(power <= 0) can never reach 1/255
     const float tau = 2.0f * __logf(255.0f * o) * 1.001f + 1e-3f;
     const float det = A * C - B * B;
-    if (!(det > 0.0f)) return make_float4(-huge, huge, -huge, huge);
+    if (!(det > 0.0f)) return 0xffu;
     const float ex = sqrtf(tau * C / det) * 1.001f + 0.01f;
     const float ey = sqrtf(tau * A / det) * 1.001f + 0.01f;
-    if (!(ex == ex) || !(ey == ey)) return make_float4(-huge, huge, -huge, huge);
-    return make_float4(a.x - ex, a.x + ex, a.y - ey, a.y + ey);
+    if (!(ex == ex) || !(ey == ey)) return 0xffu;
+    const float x0 = a.x - ex - tile_x0, x1 = a.x + ex - tile_x0;   // relative to the tile origin
+    const float y0 = a.y - ey - tile_y0, y1 = a.y + ey - tile_y0;
+    uint32_t xb = 0, m = 0;
+    if (x1 >= 0.f && x0 <= 7.f) xb |= 1u;
+    if (x1 >= 8.f && x0 <= 15.f) xb |= 2u;
+#pragma unroll
+    for (int sy = 0; sy < 4; ++sy)
+        if (y1 >= (float)(4 * sy) && y0 <= (float)(4 * sy + 3)) m |= xb << (2 * sy);
+    return m;
+}
+
+// Build this warp's compacted list of batch slots (order preserved). Returns its length.
+__device__ __forceinline__ int rdg_compact(Staged& sm, int cnt, int warp, int lane) {
+    int n_w = 0;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int g = 0; g < BATCH / 32; ++g) {
+        const int j = g * 32 + lane;
+        const bool bit = (j < cnt) && ((sm.wm[j] >> warp) & 1u);
+        const unsigned m = __ballot_sync(0xffffffffu, bit);
+        if (bit) sm.list[warp][n_w + __popc(m & lt)] = (uint8_t)j;
+        n_w += __popc(m);
+    }
+    __syncwarp();
+    return n_w;
 }
 
 __global__ void __launch_bounds__(BATCH) blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
@@ -62,11 +92,10 @@ __global__ void __launch_bounds__(BATCH) blend_fwd_kernel(const uint2* __restric
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wx0 = tx * RDG_TILE + (warp & 1) * 8, wy0 = ty * RDG_TILE + (warp >> 1) * 4;
-    const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
+    const int pxi = tx * RDG_TILE + (warp & 1) * 8 + (lane & 7), pyi = ty * RDG_TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = pxi < W && pyi < H;
     const float pixx = (float)pxi, pixy = (float)pyi;
-    const float fx0 = (float)wx0, fx1 = (float)(wx0 + 7), fy0 = (float)wy0, fy1 = (float)(wy0 + 3);
+    const float tile_x0 = (float)(tx * RDG_TILE), tile_y0 = (float)(ty * RDG_TILE);
 
     const uint2 range = ranges[tile];
     const int n_g = (int)(range.y - range.x);
@@ -85,18 +114,18 @@ __global__ void __launch_bounds__(BATCH) blend_fwd_kernel(const uint2* __restric
             sm.a[threadIdx.x] = a;
             sm.b[threadIdx.x] = b;
             sm.c[threadIdx.x] = p2[id];
-            sm.bb[threadIdx.x] = rdg_bbox(a, b);
+            sm.wm[threadIdx.x] = (uint8_t)rdg_warp_mask(a, b, tile_x0, tile_y0);
         }
         __syncthreads();
         const int cnt = min(BATCH, n_g - r * BATCH);
-        for (int j = 0; j < cnt; ++j) {
-            const float4 bb = sm.bb[j];
-            if (bb.y < fx0 || bb.x > fx1 || bb.w < fy0 || bb.z > fy1) continue;  // warp-uniform reject
-            if (done) continue;
+        if (__all_sync(0xffffffffu, done)) continue;     // this warp's 32 pixels are saturated
+        const int n_w = rdg_compact(sm, cnt, warp, lane);
+        for (int i = 0; i < n_w; ++i) {
+            const int j = sm.list[warp][i];
             const float4 a = sm.a[j];
             const float4 b = sm.b[j];
             float G, alpha;
-            if (!rdg_alpha(a.x - pixx, a.y - pixy, a.z, a.w, b.x, b.y, G, alpha)) continue;
+            if (done || !rdg_alpha(a.x - pixx, a.y - pixy, a.z, a.w, b.x, b.y, G, alpha)) continue;
             const float test_T = T * (1.0f - alpha);
             if (test_T < RDG_T_STOP) { done = true; continue; }
             const float2 c = sm.c[j];
@@ -124,6 +153,48 @@ __global__ void __launch_bounds__(BATCH) blend_fwd_kernel(const uint2* __restric
 // ---------------------------------------------------------------- backward ----
 #define NACC 12   // dpx dpy dA dB dC dop dr dg db ddepth pad pad
 
+// Reduce-scatter of ten per-lane values over the warp in 12 shuffles.  On return the lane
+// rdg_rs10_owner(k) holds the warp total of v[k] in the returned register.
+__device__ __forceinline__ float rdg_reduce_scatter10(const float* v, int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    float a[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float keep = b4 ? v[i + 5] : v[i], send = b4 ? v[i] : v[i + 5];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    float q0, q1, q2;
+    {
+        const float k0 = b3 ? a[1] : a[0], s0 = b3 ? a[0] : a[1];
+        const float k1 = b3 ? a[3] : a[2], s1 = b3 ? a[2] : a[3];
+        q0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
+        q1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
+        q2 = a[4] + __shfl_xor_sync(0xffffffffu, a[4], 8);
+    }
+    float c0, c1;
+    {
+        const float k = b2 ? q1 : q0, s = b2 ? q0 : q1;
+        c0 = k + __shfl_xor_sync(0xffffffffu, s, 4);
+        c1 = q2 + __shfl_xor_sync(0xffffffffu, q2, 4);
+    }
+    float d;
+    {
+        const float k = b1 ? c1 : c0, s = b1 ? c0 : c1;
+        d = k + __shfl_xor_sync(0xffffffffu, s, 2);
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+
+// value index owned by a lane after rdg_reduce_scatter10, or -1 (only lanes with bit0 == 0 own)
+__device__ __forceinline__ int rdg_rs10_index(int lane) {
+    if (lane & 1) return -1;
+    const int hi = (lane & 16) ? 5 : 0;
+    if (lane & 2) return ((lane & 12) == 0) ? hi + 4 : -1;          // lanes 2, 18
+    if (lane & 4) return hi + ((lane & 8) ? 3 : 2);                 // lanes 4, 12, 20, 28
+    return hi + ((lane & 8) ? 1 : 0);                               // lanes 0, 8, 16, 24
+}
+
 __global__ void __launch_bounds__(BATCH) blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
                                                           const float4* __restrict__ p0, const float4* __restrict__ p1,
                                                           const float2* __restrict__ p2, const float* __restrict__ bg,
@@ -133,15 +204,14 @@ __global__ void __launch_bounds__(BATCH) blend_bwd_kernel(const uint2* __restric
                                                           const float* __restrict__ dL_dalpha, float* __restrict__ acc) {
     __shared__ Staged sm;
     __shared__ __align__(16) float sacc[BATCH][NACC];
-    __shared__ uint32_t smax[BATCH / 32];
+    __shared__ uint32_t smax[NWARP];
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wx0 = tx * RDG_TILE + (warp & 1) * 8, wy0 = ty * RDG_TILE + (warp >> 1) * 4;
-    const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
+    const int pxi = tx * RDG_TILE + (warp & 1) * 8 + (lane & 7), pyi = ty * RDG_TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = pxi < W && pyi < H;
     const float pixx = (float)pxi, pixy = (float)pyi;
-    const float fx0 = (float)wx0, fx1 = (float)(wx0 + 7), fy0 = (float)wy0, fy1 = (float)(wy0 + 3);
+    const float tile_x0 = (float)(tx * RDG_TILE), tile_y0 = (float)(ty * RDG_TILE);
     const size_t pix = (size_t)pyi * W + pxi, hw = (size_t)H * W;
 
     const uint2 range = ranges[tile];
@@ -158,80 +228,83 @@ __global__ void __launch_bounds__(BATCH) blend_bwd_kernel(const uint2* __restric
     const float bg_dot = bg[0] * gr + bg[1] * gg + bg[2] * gb;
 
     // the CTA only has to walk back from the deepest contributor of any of its pixels
-    uint32_t m = __reduce_max_sync(0xffffffffu, my_last);
-    if (lane == 0) smax[warp] = m;
+    const uint32_t warp_last = __reduce_max_sync(0xffffffffu, my_last);
+    if (lane == 0) smax[warp] = warp_last;
     for (int k = threadIdx.x; k < BATCH * NACC; k += BATCH) (&sacc[0][0])[k] = 0.f;
     __syncthreads();
     uint32_t max_last = 0;
 #pragma unroll
-    for (int k = 0; k < BATCH / 32; ++k) max_last = max(max_last, smax[k]);
+    for (int k = 0; k < NWARP; ++k) max_last = max(max_last, smax[k]);
     max_last = min(max_last, (uint32_t)n_g);
     if (max_last == 0) return;
 
     float T = T_final;
     float rec_r = 0.f, rec_g = 0.f, rec_b = 0.f, rec_d = 0.f, rec_a = 0.f;
     float last_alpha = 0.f, last_r = 0.f, last_g = 0.f, last_b = 0.f, last_d = 0.f;
+    const int own_k = rdg_rs10_index(lane);
 
     const int rounds = ((int)max_last + BATCH - 1) / BATCH;
     for (int r = 0; r < rounds; ++r) {
         // batch r covers list positions pos = max_last-1 - (r*BATCH + slot), slot = 0..cnt-1 (back to front)
         const int cnt = min(BATCH, (int)max_last - r * BATCH);
+        const int pos0 = (int)max_last - 1 - r * BATCH;       // list position of slot 0
         __syncthreads();
         if ((int)threadIdx.x < cnt) {
-            const int pos = (int)max_last - 1 - (r * BATCH + (int)threadIdx.x);
-            const uint32_t id = vals[range.x + pos];
+            const uint32_t id = vals[range.x + pos0 - (int)threadIdx.x];
             const float4 a = p0[id], b = p1[id];
             sm.id[threadIdx.x] = id;
             sm.a[threadIdx.x] = a;
             sm.b[threadIdx.x] = b;
             sm.c[threadIdx.x] = p2[id];
-            sm.bb[threadIdx.x] = rdg_bbox(a, b);
+            sm.wm[threadIdx.x] = (uint8_t)rdg_warp_mask(a, b, tile_x0, tile_y0);
         }
         __syncthreads();
-        for (int j = 0; j < cnt; ++j) {
-            const float4 bb = sm.bb[j];
-            if (bb.y < fx0 || bb.x > fx1 || bb.w < fy0 || bb.z > fy1) continue;  // warp-uniform reject
-            const uint32_t pos = max_last - 1 - (uint32_t)(r * BATCH + j);
-            const float4 a = sm.a[j];
-            const float4 b = sm.b[j];
-            const float dx = a.x - pixx, dy = a.y - pixy;
-            float G = 0.f, alpha = 0.f;
-            bool on = pos < my_last;
-            if (on) on = rdg_alpha(dx, dy, a.z, a.w, b.x, b.y, G, alpha);
-            if (!__any_sync(0xffffffffu, on)) continue;
-            float v[10];
+        // slots whose position is beyond this warp's deepest contributor cannot contribute
+        const int first_slot = max(0, pos0 - (int)warp_last + 1);
+        if (first_slot < cnt) {
+            const int n_w = rdg_compact(sm, cnt, warp, lane);
+            for (int i = 0; i < n_w; ++i) {
+                const int j = sm.list[warp][i];
+                if (j < first_slot) continue;
+                const uint32_t pos = (uint32_t)(pos0 - j);
+                const float4 a = sm.a[j];
+                const float4 b = sm.b[j];
+                const float dx = a.x - pixx, dy = a.y - pixy;
+                float G = 0.f, alpha = 0.f;
+                bool on = pos < my_last;
+                if (on) on = rdg_alpha(dx, dy, a.z, a.w, b.x, b.y, G, alpha);
+                if (!__any_sync(0xffffffffu, on)) continue;
+                float v[10];
 #pragma unroll
-            for (int k = 0; k < 10; ++k) v[k] = 0.f;
-            if (on) {
-                const float2 c = sm.c[j];
-                T = T / (1.0f - alpha);
-                const float wgt = alpha * T;
-                rec_r = last_alpha * last_r + (1.f - last_alpha) * rec_r;
-                rec_g = last_alpha * last_g + (1.f - last_alpha) * rec_g;
-                rec_b = last_alpha * last_b + (1.f - last_alpha) * rec_b;
-                rec_d = last_alpha * last_d + (1.f - last_alpha) * rec_d;
-                rec_a = last_alpha + (1.f - last_alpha) * rec_a;
-                last_r = b.z; last_g = b.w; last_b = c.x; last_d = c.y;
-                float dL_da = (b.z - rec_r) * gr + (b.w - rec_g) * gg + (c.x - rec_b) * gb + (c.y - rec_d) * gd + (1.f - rec_a) * ga;
-                dL_da *= T;
-                last_alpha = alpha;
-                dL_da += (-T_final / (1.f - alpha)) * bg_dot;
-                const float dL_dG = b.y * dL_da;
-                const float gdx = G * dx, gdy = G * dy;
-                v[0] = dL_dG * (-gdx * a.z - gdy * a.w);      // d/dpx (pixel units)
-                v[1] = dL_dG * (-gdy * b.x - gdx * a.w);      // d/dpy
-                v[2] = -0.5f * gdx * dx * dL_dG;              // dA
-                v[3] = -gdx * dy * dL_dG;                     // dB (B enters `power` once)
-                v[4] = -0.5f * gdy * dy * dL_dG;              // dC
-                v[5] = G * dL_da;                             // dopacity
-                v[6] = wgt * gr; v[7] = wgt * gg; v[8] = wgt * gb;   // drgb
-                v[9] = wgt * gd;                              // ddepth
-            }
-#pragma unroll
-            for (int k = 0; k < 10; ++k) v[k] = warp_sum(v[k]);
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < 10; ++k) atomicAdd(&sacc[j][k], v[k]);
+                for (int k = 0; k < 10; ++k) v[k] = 0.f;
+                if (on) {
+                    const float2 c = sm.c[j];
+                    T = T / (1.0f - alpha);
+                    const float wgt = alpha * T;
+                    const float om = 1.f - last_alpha;
+                    rec_r = last_alpha * last_r + om * rec_r;
+                    rec_g = last_alpha * last_g + om * rec_g;
+                    rec_b = last_alpha * last_b + om * rec_b;
+                    rec_d = last_alpha * last_d + om * rec_d;
+                    rec_a = last_alpha + om * rec_a;
+                    last_r = b.z; last_g = b.w; last_b = c.x; last_d = c.y;
+                    float dL_da = (b.z - rec_r) * gr + (b.w - rec_g) * gg + (c.x - rec_b) * gb + (c.y - rec_d) * gd + (1.f - rec_a) * ga;
+                    dL_da *= T;
+                    last_alpha = alpha;
+                    dL_da += (-T_final / (1.f - alpha)) * bg_dot;
+                    const float dL_dG = b.y * dL_da;
+                    const float gdx = G * dx, gdy = G * dy;
+                    v[0] = dL_dG * (-gdx * a.z - gdy * a.w);      // d/dpx (pixel units)
+                    v[1] = dL_dG * (-gdy * b.x - gdx * a.w);      // d/dpy
+                    v[2] = -0.5f * gdx * dx * dL_dG;              // dA
+                    v[3] = -gdx * dy * dL_dG;                     // dB (B enters `power` once)
+                    v[4] = -0.5f * gdy * dy * dL_dG;              // dC
+                    v[5] = G * dL_da;                             // dopacity
+                    v[6] = wgt * gr; v[7] = wgt * gg; v[8] = wgt * gb;   // drgb
+                    v[9] = wgt * gd;                              // ddepth
+                }
+                const float tot = rdg_reduce_scatter10(v, lane);
+                if (own_k >= 0) atomicAdd(&sacc[j][own_k], tot);
             }
         }
         __syncthreads();

@@ -354,6 +354,7 @@ def test_sync_free_mode_matches_and_reports_overflow():
     b = _run_boundary(acts, cam, bg, 1)["out"][0]
     assert torch.equal(a, b)
     torch.cuda.synchronize()
+    engine._capacity[0]["pending"] = None     # (the lazy check would otherwise re-grow the capacity)
     engine._capacity[0]["cap"] = 128          # force an overflow on the next sync-free frame
     _run_boundary(acts, cam, bg, 1)
     with pytest.raises(RuntimeError, match="truncated"):
