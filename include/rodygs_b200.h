@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RDG_ABI_VERSION 1
+#define RDG_ABI_VERSION 2
 #define RDG_TILE 16
 #define RDG_NUM_BASIS_MAX 16
 
@@ -76,6 +76,12 @@ typedef struct RdgScene {
     const float* basis_t;        /* [num_basis,7]  B(t) for this view's time */
     const float* table;          /* [T,num_basis,7] B at every training time (get_total_motion_table) */
     float spatial_lr_scale;
+    /* optional CSR of the dynamic Gaussians by birth frame (built once per time_ind by the host:
+     * frame_order = stable argsort(time_ind) [n_dynamic], frame_offsets [T+1]).  With it the backward
+     * pass reduces dL/dtable per frame without atomics on the hot path; without it (NULL) it falls
+     * back to shared-memory atomics. */
+    const int32_t* frame_order;
+    const int32_t* frame_offsets;
 } RdgScene;
 
 typedef struct RdgView {
@@ -135,6 +141,7 @@ typedef struct RdgSceneGrad {
     float* motion_coeff;     /* [n_dynamic,num_basis] */
     float* table;            /* [T,num_basis,7] accumulated (+=) */
     float* basis_t;          /* [num_basis,7]   accumulated (+=) */
+    float* g7_scratch;       /* [n_dynamic,8] scratch, required when scene.frame_order is set */
 } RdgSceneGrad;
 
 int rdg_abi_version(void);

@@ -26,7 +26,8 @@ class RdgScene(C.Structure):
     _fields_ = [("n_static", C.c_int64), ("n_dynamic", C.c_int64), ("st", RdgSet), ("dy", RdgSet),
                 ("raw", C.c_int32), ("colors_precomp", c_ptr), ("use_deform", C.c_int32),
                 ("num_basis", C.c_int32), ("num_times", C.c_int32), ("motion_coeff", c_ptr),
-                ("time_ind", c_ptr), ("basis_t", c_ptr), ("table", c_ptr), ("spatial_lr_scale", C.c_float)]
+                ("time_ind", c_ptr), ("basis_t", c_ptr), ("table", c_ptr), ("spatial_lr_scale", C.c_float),
+                ("frame_order", c_ptr), ("frame_offsets", c_ptr)]
 
 
 class RdgView(C.Structure):
@@ -56,7 +57,7 @@ class RdgSetGrad(C.Structure):
 
 class RdgSceneGrad(C.Structure):
     _fields_ = [("st", RdgSetGrad), ("dy", RdgSetGrad), ("colors_precomp", c_ptr), ("means2D", c_ptr),
-                ("viewmatrix", c_ptr), ("motion_coeff", c_ptr), ("table", c_ptr), ("basis_t", c_ptr)]
+                ("viewmatrix", c_ptr), ("motion_coeff", c_ptr), ("table", c_ptr), ("basis_t", c_ptr), ("g7_scratch", c_ptr)]
 
 
 # every symbol include/rodygs_b200.h declares: name -> (restype, argtypes)
@@ -101,7 +102,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.rdg_abi_version() != 1:
+    if lib.rdg_abi_version() != 2:
         raise RuntimeError("librodygs_b200.so ABI version mismatch")
     _lib = lib
     return lib

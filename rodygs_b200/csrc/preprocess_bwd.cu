@@ -4,11 +4,17 @@
 // SURVEY.md §8 row a10, App. A.6-A.7; checked against autograd of the oracle.
 //
 // HBM-bound: reads 48 B acc + the forward inputs again, writes 44 B + 12*K B (dSH)
-// + 12 B (means2D sink) [+ 64 B dcoeff] per Gaussian.  dSH rows are staged through
-// shared memory so that both the SH read and the dSH write are fully coalesced.
-// dL/dtable[T,K,7] is accumulated in shared memory per (persistent) CTA and flushed
-// once; dL/dB(t) = -sum_t dL/dtable[t] falls out of the same flush.
+// + 12 B (means2D sink) [+ 64 B dcoeff + 32 B g7] per Gaussian.
+//
+// B200 mapping: same chunking as the forward kernel (256 Gaussians of ONE model per
+// chunk).  The chunk's SH rows arrive by one TMA bulk load, every thread turns its row
+// into the dSH row in place, and the 46 KB of gradients leave by one TMA bulk store -
+// both directions fully coalesced without LSU instructions.  The motion-table gradient
+// dL/dtable[t] = -sum_{i born at t} c_i (x) g_i is NOT accumulated with atomics here:
+// the kernel writes g_i (7 floats) per dynamic Gaussian and `dtable_kernel` reduces them
+// per birth frame over a CSR built once by the host (frame_order / frame_offsets).
 #include "scene.cuh"
+#include "tma.cuh"
 
 #define SH_ROW 45
 #define NACC 12
@@ -19,23 +25,24 @@ struct PreBwdParams {
     RdgGeom geom;
     RdgSceneGrad gr;
     const float* acc;
-    int diff_in_smem;
-    int dtab_in_smem;
+    int use_tma;
+    int dtab_atomic;   // no CSR: accumulate dL/dtable with global atomics from this kernel
 };
 
-__device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z, float* bx, float* by, float* bz) {
+template <int DEG>
+__device__ __forceinline__ void sh_basis_grad(float x, float y, float z, float* bx, float* by, float* bz) {
     bx[0] = by[0] = bz[0] = 0.f;
-    if (deg > 0) {
+    if (DEG > 0) {
         bx[1] = 0.f;         by[1] = -RDG_SH_C1; bz[1] = 0.f;
         bx[2] = 0.f;         by[2] = 0.f;        bz[2] = RDG_SH_C1;
         bx[3] = -RDG_SH_C1;  by[3] = 0.f;        bz[3] = 0.f;
-        if (deg > 1) {
+        if (DEG > 1) {
             bx[4] = RDG_SH_C2_0 * y;          by[4] = RDG_SH_C2_0 * x;          bz[4] = 0.f;
             bx[5] = 0.f;                      by[5] = RDG_SH_C2_1 * z;          bz[5] = RDG_SH_C2_1 * y;
             bx[6] = RDG_SH_C2_2 * -2.f * x;   by[6] = RDG_SH_C2_2 * -2.f * y;   bz[6] = RDG_SH_C2_2 * 4.f * z;
             bx[7] = RDG_SH_C2_3 * z;          by[7] = 0.f;                      bz[7] = RDG_SH_C2_3 * x;
             bx[8] = RDG_SH_C2_4 * 2.f * x;    by[8] = RDG_SH_C2_4 * -2.f * y;   bz[8] = 0.f;
-            if (deg > 2) {
+            if (DEG > 2) {
                 const float xx = x * x, yy = y * y, zz = z * z;
                 bx[9] = RDG_SH_C3_0 * 6.f * x * y;       by[9] = RDG_SH_C3_0 * (3.f * xx - 3.f * yy);      bz[9] = 0.f;
                 bx[10] = RDG_SH_C3_1 * y * z;            by[10] = RDG_SH_C3_1 * x * z;                     bz[10] = RDG_SH_C3_1 * x * y;
@@ -49,21 +56,18 @@ __device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z
     }
 }
 
-template <bool RAW>
-__global__ void __launch_bounds__(RDG_BLOCK) preprocess_bwd_kernel(const PreBwdParams p) {
-    extern __shared__ float smem[];
+template <bool RAW, int DEG>
+__global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreBwdParams p) {
+    extern __shared__ __align__(128) float smem[];
+    constexpr int K = (DEG + 1) * (DEG + 1);
+    constexpr int NREST = 3 * (K - 1);
     const RdgScene& sc = p.sc;
-    const int64_t N = sc.n_static + sc.n_dynamic;
-    const int deg = p.view.sh_degree;
-    const int K = (deg + 1) * (deg + 1);
     const bool use_sh = sc.colors_precomp == nullptr;
     const bool deform = RAW && sc.use_deform && sc.n_dynamic > 0;
-    const int per_t = sc.num_basis * 7;
-    const int tab_n = deform ? sc.num_times * per_t : 0;
-    float* sh_s = smem;                                    // [256][SH_ROW] in: SH rest coefficients, out: their gradients
-    float* diff_s = sh_s + RDG_BLOCK * SH_ROW;             // [T][K][7]
-    float* dtab_s = diff_s + (p.diff_in_smem ? tab_n : 0);  // [T][K][7]
+    float* sh_s = smem;                       // [256][SH_ROW] in: SH rest coefficients, out: their gradients
+    float* bt_s = smem + RDG_BLOCK * SH_ROW;  // [16*7] B(t)
     __shared__ float red_s[RDG_BLOCK / 32][16];
+    __shared__ __align__(8) uint64_t bar;
 
     RdgCam cam;
     rdg_load_cam(cam, p.view.viewmatrix, p.view.projmatrix, p.view.tanfovx, p.view.tanfovy, p.view.width, p.view.height);
@@ -72,15 +76,9 @@ __global__ void __launch_bounds__(RDG_BLOCK) preprocess_bwd_kernel(const PreBwdP
     const float* V = cam.V;
     const float* P = cam.P;
 
-    const float* diff = nullptr;
-    if (deform) {
-        if (p.diff_in_smem) {
-            for (int e = threadIdx.x; e < tab_n; e += RDG_BLOCK) diff_s[e] = sc.basis_t[e % per_t] - sc.table[e];
-            diff = diff_s;
-        }
-        if (p.dtab_in_smem)
-            for (int e = threadIdx.x; e < tab_n; e += RDG_BLOCK) dtab_s[e] = 0.f;
-    }
+    if (deform)
+        for (int e = threadIdx.x; e < sc.num_basis * 7; e += RDG_BLOCK) bt_s[e] = sc.basis_t[e];
+    if (threadIdx.x == 0) rdg_mbar_init(&bar, 1);
     __syncthreads();
 
     float poseV[12];   // dL/dV rows 0..2 (row-major), this thread's partial sum
@@ -89,50 +87,61 @@ __global__ void __launch_bounds__(RDG_BLOCK) preprocess_bwd_kernel(const PreBwdP
     for (int k = 0; k < 12; ++k) poseV[k] = 0.f;
 
     const int lane = threadIdx.x & 31;
-    const int64_t n_chunks = (N + RDG_BLOCK - 1) / RDG_BLOCK;
-    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        const int64_t base = chunk * RDG_BLOCK;
-        const int cnt = (int)min((int64_t)RDG_BLOCK, N - base);
-        const int64_t i = base + threadIdx.x;
-        const bool valid = i < N;
+    const int64_t cs = (sc.n_static + RDG_BLOCK - 1) / RDG_BLOCK, cd = (sc.n_dynamic + RDG_BLOCK - 1) / RDG_BLOCK;
+    uint32_t phase = 0;
+    bool store_pending = false;
+    for (int64_t chunk = blockIdx.x; chunk < cs + cd; chunk += gridDim.x) {
+        const bool dyn = chunk >= cs;
+        const RdgSet& set = dyn ? sc.dy : sc.st;
+        const RdgSetGrad& gs = dyn ? p.gr.dy : p.gr.st;
+        const int64_t lbase = (dyn ? chunk - cs : chunk) * RDG_BLOCK;
+        const int64_t n_set = dyn ? sc.n_dynamic : sc.n_static;
+        const int cnt = (int)min((int64_t)RDG_BLOCK, n_set - lbase);
+        const bool valid = (int)threadIdx.x < cnt;
+        const int64_t local = lbase + threadIdx.x;
+        const int64_t i = (dyn ? sc.n_static : 0) + local;
         const int radius = valid ? p.geom.radii[i] : 0;
         const bool vis = radius > 0;
 
-        // ---- stage SH rest rows (visible Gaussians only need them, but the copy is coalesced) ----
-        __syncthreads();
-        if (use_sh && K > 1) {
-            const int nrest = 3 * (K - 1);
-            const int tot = cnt * nrest;
-            for (int e = threadIdx.x; e < tot; e += RDG_BLOCK) {
-                const int g = e / nrest, k = e - g * nrest;
-                const int64_t gi = base + g;
-                const bool dy = gi >= sc.n_static;
-                const RdgSet& set = dy ? sc.dy : sc.st;
-                const int64_t l = dy ? gi - sc.n_static : gi;
-                sh_s[g * SH_ROW + k] = set.sh_rest[l * set.sh_rest_stride + k];
+        // ---- stage the SH rest rows ----
+        const bool full_rows = use_sh && set.sh_rest_stride == SH_ROW;
+        const bool tma_in = full_rows && p.use_tma && NREST == SH_ROW && (cnt & 3) == 0;
+        const bool tma_out = full_rows && p.use_tma && gs.sh_rest != nullptr && (cnt & 3) == 0;
+        if (threadIdx.x == 0 && store_pending) { rdg_bulk_store_wait_read(); store_pending = false; }
+        __syncthreads();   // previous chunk fully written out / read
+        if (use_sh && NREST > 0) {
+            if (tma_in) {
+                if (threadIdx.x == 0) {
+                    rdg_fence_proxy_async();
+                    rdg_bulk_load(sh_s, set.sh_rest + lbase * SH_ROW, (uint32_t)(cnt * SH_ROW * sizeof(float)), &bar);
+                }
+            } else {
+                const int stride = set.sh_rest_stride;
+                const float* src = set.sh_rest + lbase * stride;
+                for (int e = threadIdx.x; e < cnt * NREST; e += RDG_BLOCK) {
+                    const int g = e / NREST, k = e - g * NREST;
+                    sh_s[g * SH_ROW + k] = src[(int64_t)g * stride + k];
+                }
             }
         }
-        __syncthreads();
 
         RdgAct a;
-        a.dyn = false; a.local = 0; a.ti = 0;
+        a.dyn = dyn; a.local = local; a.ti = 0;
         float dmean[3] = {0.f, 0.f, 0.f}, dscale[3] = {0.f, 0.f, 0.f}, dquat[4] = {0.f, 0.f, 0.f, 0.f};
         float dop = 0.f, ddc[3] = {0.f, 0.f, 0.f}, dm2[2] = {0.f, 0.f};
+        float grgb[3] = {0.f, 0.f, 0.f};
         float* my_sh = sh_s + threadIdx.x * SH_ROW;
-        if (valid) {
-            a.dyn = i >= sc.n_static;
-            a.local = a.dyn ? i - sc.n_static : i;
-        }
         if (vis) {
-            rdg_fetch<RAW>(sc, i, diff, a);
+            rdg_fetch<RAW>(sc, dyn, local, bt_s, a);
             RdgProj pr;
             rdg_project(cam, a, p.view.scale_modifier, pr);
-            const float4 g0 = reinterpret_cast<const float4*>(p.acc)[i * 3 + 0];
-            const float4 g1 = reinterpret_cast<const float4*>(p.acc)[i * 3 + 1];
-            const float4 g2 = reinterpret_cast<const float4*>(p.acc)[i * 3 + 2];
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.acc) + i * 3 + 0);
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.acc) + i * 3 + 1);
+            const float4 g2 = __ldg(reinterpret_cast<const float4*>(p.acc) + i * 3 + 2);
             const float gA = g0.z, gB = g0.w, gC = g1.x;
-            float grgb[3] = {g1.z, g1.w, g2.x};
+            grgb[0] = g1.z; grgb[1] = g1.w; grgb[2] = g2.x;
             const float gdepth = g2.y;
+            dop = g1.y;
 
             // ---- projection path ----
             const float dndcx = g0.x * 0.5f * cam.W, dndcy = g0.y * 0.5f * cam.H;
@@ -217,8 +226,14 @@ __global__ void __launch_bounds__(RDG_BLOCK) preprocess_bwd_kernel(const PreBwdP
                 const float dtp = dt_pose[r] + cov_pose * dt_cov[r];
                 poseV[r * 4 + 0] += dtp * a.x; poseV[r * 4 + 1] += dtp * a.y; poseV[r * 4 + 2] += dtp * a.z; poseV[r * 4 + 3] += dtp;
             }
+        }
 
-            // ---- colour ----
+        // ---- colour: needs the staged SH rows ----
+        if (use_sh && NREST > 0) {
+            if (tma_in) { rdg_mbar_wait(&bar, phase & 1u); ++phase; }
+            else __syncthreads();
+        }
+        if (vis) {
             if (use_sh) {
                 const unsigned cl = p.geom.clamped[i];
 #pragma unroll
@@ -227,17 +242,19 @@ __global__ void __launch_bounds__(RDG_BLOCK) preprocess_bwd_kernel(const PreBwdP
                 const float len2 = dx * dx + dy * dy + dz * dz;
                 const float inv = 1.0f / sqrtf(len2);
                 dx *= inv; dy *= inv; dz *= inv;
-                float b[16], bx[16], by[16], bz[16];
-                rdg_sh_basis(deg, dx, dy, dz, b);
-                sh_basis_grad(deg, dx, dy, dz, bx, by, bz);
+                float b[K], bx[K], by[K], bz[K];
+                rdg_sh_basis<DEG>(dx, dy, dz, b);
+                sh_basis_grad<DEG>(dx, dy, dz, bx, by, bz);
                 ddc[0] = b[0] * grgb[0]; ddc[1] = b[0] * grgb[1]; ddc[2] = b[0] * grgb[2];
                 float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+#pragma unroll
                 for (int k = 1; k < K; ++k) {
                     float* row = my_sh + (k - 1) * 3;
                     const float w = row[0] * grgb[0] + row[1] * grgb[1] + row[2] * grgb[2];
                     ddx += bx[k] * w; ddy += by[k] * w; ddz += bz[k] * w;
                     row[0] = b[k] * grgb[0]; row[1] = b[k] * grgb[1]; row[2] = b[k] * grgb[2];
                 }
+#pragma unroll
                 for (int k = K; k < 16; ++k) { float* row = my_sh + (k - 1) * 3; row[0] = row[1] = row[2] = 0.f; }
                 const float dot = dx * ddx + dy * ddy + dz * ddz;
                 const float gx_ = (ddx - dx * dot) * inv, gy_ = (ddy - dy * dot) * inv, gz_ = (ddz - dz * dot) * inv;
@@ -246,97 +263,111 @@ __global__ void __launch_bounds__(RDG_BLOCK) preprocess_bwd_kernel(const PreBwdP
             } else {
                 ddc[0] = grgb[0]; ddc[1] = grgb[1]; ddc[2] = grgb[2];
             }
-            dop = g1.y;
         } else if (valid && use_sh) {
+#pragma unroll
             for (int k = 0; k < SH_ROW; ++k) my_sh[k] = 0.f;
         }
 
         // ---- through the activations / deformation, and write out ----
-        const RdgSetGrad& gs = a.dyn ? p.gr.dy : p.gr.st;
         float g7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         bool has_def = false;
         if (valid) {
             if (p.gr.means2D) { float* o = p.gr.means2D + i * 3; o[0] = dm2[0]; o[1] = dm2[1]; o[2] = 0.f; }
-            if (gs.xyz) { float* o = gs.xyz + a.local * 3; o[0] = dmean[0]; o[1] = dmean[1]; o[2] = dmean[2]; }
-            if (RAW) {
-                if (vis) {
+            if (gs.xyz) { float* o = gs.xyz + local * 3; o[0] = dmean[0]; o[1] = dmean[1]; o[2] = dmean[2]; }
+            if (RAW && vis) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) dscale[k] *= a.s[k];
-                    dop *= a.op * (1.0f - a.op);
-                    has_def = deform && a.dyn;
-                    if (has_def) {
-                        g7[0] = dmean[0] * sc.spatial_lr_scale; g7[1] = dmean[1] * sc.spatial_lr_scale; g7[2] = dmean[2] * sc.spatial_lr_scale;
-                        g7[3] = dquat[0]; g7[4] = dquat[1]; g7[5] = dquat[2]; g7[6] = dquat[3];
-                    }
-                    const float dot = a.qn[0] * dquat[0] + a.qn[1] * dquat[1] + a.qn[2] * dquat[2] + a.qn[3] * dquat[3];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) dquat[k] = (dquat[k] - a.qn[k] * dot) * a.qinv;
+                for (int k = 0; k < 3; ++k) dscale[k] *= a.s[k];
+                dop *= a.op * (1.0f - a.op);
+                has_def = deform && dyn;
+                if (has_def) {
+                    g7[0] = dmean[0] * sc.spatial_lr_scale; g7[1] = dmean[1] * sc.spatial_lr_scale; g7[2] = dmean[2] * sc.spatial_lr_scale;
+                    g7[3] = dquat[0]; g7[4] = dquat[1]; g7[5] = dquat[2]; g7[6] = dquat[3];
                 }
+                const float dot = a.qn[0] * dquat[0] + a.qn[1] * dquat[1] + a.qn[2] * dquat[2] + a.qn[3] * dquat[3];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dquat[k] = (dquat[k] - a.qn[k] * dot) * a.qinv;
             }
-            if (gs.scaling) { float* o = gs.scaling + a.local * 3; o[0] = dscale[0]; o[1] = dscale[1]; o[2] = dscale[2]; }
-            if (gs.rotation) { float* o = gs.rotation + a.local * 4; o[0] = dquat[0]; o[1] = dquat[1]; o[2] = dquat[2]; o[3] = dquat[3]; }
-            if (gs.opacity) gs.opacity[a.local] = dop;
+            if (gs.scaling) { float* o = gs.scaling + local * 3; o[0] = dscale[0]; o[1] = dscale[1]; o[2] = dscale[2]; }
+            if (gs.rotation) reinterpret_cast<float4*>(gs.rotation)[local] = make_float4(dquat[0], dquat[1], dquat[2], dquat[3]);
+            if (gs.opacity) gs.opacity[local] = dop;
             if (use_sh) {
-                if (gs.sh_dc) { float* o = gs.sh_dc + a.local * (a.dyn ? sc.dy.sh_dc_stride : sc.st.sh_dc_stride); o[0] = ddc[0]; o[1] = ddc[1]; o[2] = ddc[2]; }
+                if (gs.sh_dc) { float* o = gs.sh_dc + local * set.sh_dc_stride; o[0] = ddc[0]; o[1] = ddc[1]; o[2] = ddc[2]; }
             } else if (p.gr.colors_precomp) {
                 float* o = p.gr.colors_precomp + i * 3; o[0] = ddc[0]; o[1] = ddc[1]; o[2] = ddc[2];
             }
-            if (RAW && deform && a.dyn && p.gr.motion_coeff) {
-                float* o = p.gr.motion_coeff + a.local * sc.num_basis;
-                for (int k = 0; k < sc.num_basis; ++k) {
-                    float s = 0.f;
-                    if (has_def) {
+            if (deform && dyn) {
+                if (p.gr.motion_coeff) {
+                    float dcf[RDG_NUM_BASIS_MAX];
 #pragma unroll
-                        for (int j = 0; j < 7; ++j) s += rdg_basis_diff(sc, diff, a.ti, k, j) * g7[j];
+                    for (int k = 0; k < RDG_NUM_BASIS_MAX; ++k) dcf[k] = 0.f;
+                    if (has_def) {
+                        if (sc.num_basis == RDG_NUM_BASIS_MAX) {
+                            const float4* row4 = reinterpret_cast<const float4*>(sc.table + (int64_t)a.ti * 112);
+#pragma unroll
+                            for (int q = 0; q < 28; ++q) {
+                                const float4 v = __ldg(row4 + q);
+                                const float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                                for (int m = 0; m < 4; ++m) {
+                                    const int e = 4 * q + m;
+                                    dcf[e / 7] += (bt_s[e] - r[m]) * g7[e % 7];
+                                }
+                            }
+                        } else {
+                            for (int k = 0; k < sc.num_basis; ++k)
+#pragma unroll
+                                for (int j = 0; j < 7; ++j) dcf[k] += rdg_basis_diff(sc, bt_s, a.ti, k, j) * g7[j];
+                        }
                     }
-                    o[k] = s;
+                    float* o = p.gr.motion_coeff + local * sc.num_basis;
+                    if (sc.num_basis == RDG_NUM_BASIS_MAX) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            reinterpret_cast<float4*>(o)[q] = make_float4(dcf[4 * q], dcf[4 * q + 1], dcf[4 * q + 2], dcf[4 * q + 3]);
+                    } else {
+                        for (int k = 0; k < sc.num_basis; ++k) o[k] = dcf[k];
+                    }
+                }
+                if (p.gr.g7_scratch) {
+                    float4* o = reinterpret_cast<float4*>(p.gr.g7_scratch + local * 8);
+                    o[0] = make_float4(g7[0], g7[1], g7[2], g7[3]);
+                    o[1] = make_float4(g7[4], g7[5], g7[6], 0.f);
                 }
             }
         }
-        // dL/dtable[ti][k][j] -= c_k * g7[j]
-        if (deform && p.gr.table) {
-            const unsigned any = __ballot_sync(0xffffffffu, has_def);
-            if (any) {
-                const int src = __ffs(any) - 1;
-                const int ti0 = __shfl_sync(0xffffffffu, a.ti, src);
-                const bool uniform = __all_sync(0xffffffffu, !has_def || a.ti == ti0);
-                float* tab = p.dtab_in_smem ? dtab_s : p.gr.table;
-                if (uniform) {
-                    for (int k = 0; k < sc.num_basis; ++k) {
-                        const float ck = has_def ? a.c[k] : 0.f;
+        // fallback without the birth-frame CSR: dL/dtable[ti][k][j] -= c_k g7[j] with global atomics
+        if (deform && dyn && p.dtab_atomic && p.gr.table && has_def) {
+            for (int k = 0; k < sc.num_basis; ++k) {
 #pragma unroll
-                        for (int j = 0; j < 7; ++j) {
-                            const float s = warp_sum(ck * g7[j]);
-                            if (lane == 0) atomicAdd(&tab[(ti0 * sc.num_basis + k) * 7 + j], -s);
-                        }
-                    }
-                } else if (has_def) {
-                    for (int k = 0; k < sc.num_basis; ++k) {
-                        const float ck = a.c[k];
-#pragma unroll
-                        for (int j = 0; j < 7; ++j) atomicAdd(&tab[(a.ti * sc.num_basis + k) * 7 + j], -ck * g7[j]);
-                    }
+                for (int j = 0; j < 7; ++j) {
+                    const float v = a.c[k] * g7[j];
+                    atomicAdd(&p.gr.table[(a.ti * sc.num_basis + k) * 7 + j], -v);
+                    if (p.gr.basis_t) atomicAdd(&p.gr.basis_t[k * 7 + j], v);
                 }
             }
         }
 
-        // ---- coalesced write of the dSH rest rows ----
-        __syncthreads();
-        if (use_sh) {
-            const int tot = cnt * SH_ROW;
-            for (int e = threadIdx.x; e < tot; e += RDG_BLOCK) {
-                const int g = e / SH_ROW, k = e - g * SH_ROW;
-                const int64_t gi = base + g;
-                const bool dy = gi >= sc.n_static;
-                const RdgSetGrad& gset = dy ? p.gr.dy : p.gr.st;
-                if (gset.sh_rest) {
-                    const int64_t l = dy ? gi - sc.n_static : gi;
-                    const int stride = dy ? sc.dy.sh_rest_stride : sc.st.sh_rest_stride;
-                    gset.sh_rest[l * stride + k] = sh_s[e];
+        // ---- write the dSH rest rows ----
+        if (use_sh && gs.sh_rest) {
+            if (tma_out) {
+                rdg_fence_proxy_async();   // my generic-proxy writes -> visible to the async proxy
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    rdg_bulk_store(gs.sh_rest + lbase * SH_ROW, sh_s, (uint32_t)(cnt * SH_ROW * sizeof(float)));
+                    store_pending = true;
+                }
+            } else {
+                __syncthreads();
+                const int stride = set.sh_rest_stride;
+                float* dst = gs.sh_rest + lbase * stride;
+                for (int e = threadIdx.x; e < cnt * SH_ROW; e += RDG_BLOCK) {
+                    const int g = e / SH_ROW, k = e - g * SH_ROW;
+                    dst[(int64_t)g * stride + k] = sh_s[e];
                 }
             }
         }
     }
+    if (threadIdx.x == 0 && store_pending) rdg_bulk_store_wait_read();
 
     // ---- pose gradient: warp shuffle -> shared -> one atomic set per CTA ----
     if (p.gr.viewmatrix) {
@@ -368,20 +399,60 @@ __global__ void __launch_bounds__(RDG_BLOCK) preprocess_bwd_kernel(const PreBwdP
                 for (int k = 0; k < 4; ++k) atomicAdd(&p.gr.viewmatrix[k * 4 + r], t[r * 4 + k]);
         }
     }
-    // ---- flush dL/dtable, derive dL/dB(t) ----
-    if (deform && p.gr.table && p.dtab_in_smem) {
+}
+
+// dL/dtable[t][k][j] = -sum_{i : birth frame t} c_i[k] g_i[j];  dL/dB(t)[k][j] = +sum_i c_i[k] g_i[j].
+// grid (T, DT_SLICES); thread e < K*7 owns one (k, j) and accumulates in a register over the
+// frame's Gaussians, staged 64 at a time in shared memory - no atomics until the final add.
+#define DT_SLICES 8
+#define DT_TILE 64
+__global__ void __launch_bounds__(128) dtable_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ offsets,
+                                                     const float* __restrict__ coeff, const float* __restrict__ g7, int num_basis,
+                                                     float* __restrict__ dtable, float* __restrict__ dbasis) {
+    __shared__ float c_s[DT_TILE][RDG_NUM_BASIS_MAX + 1];
+    __shared__ float g_s[DT_TILE][8];
+    const int t = blockIdx.x;
+    const int beg = offsets[t], end = offsets[t + 1];
+    const int per_t = num_basis * 7;
+    const int e = threadIdx.x;
+    const int k = e / 7, j = e - k * 7;
+    float accv = 0.f;
+    for (int base = beg + blockIdx.y * DT_TILE; base < end; base += DT_SLICES * DT_TILE) {
+        const int cnt = min(DT_TILE, end - base);
         __syncthreads();
-        for (int e = threadIdx.x; e < tab_n; e += RDG_BLOCK) {
-            const float v = dtab_s[e];
-            if (v != 0.f) atomicAdd(&p.gr.table[e], v);
+        for (int x = threadIdx.x; x < cnt * num_basis; x += blockDim.x) {
+            const int g = x / num_basis, kk = x - g * num_basis;
+            c_s[g][kk] = coeff[(int64_t)order[base + g] * num_basis + kk];
         }
-        if (p.gr.basis_t) {
-            for (int e = threadIdx.x; e < per_t; e += RDG_BLOCK) {
-                float s = 0.f;
-                for (int t = 0; t < sc.num_times; ++t) s += dtab_s[t * per_t + e];
-                if (s != 0.f) atomicAdd(&p.gr.basis_t[e], -s);
-            }
+        for (int x = threadIdx.x; x < cnt * 8; x += blockDim.x) {
+            const int g = x >> 3, jj = x & 7;
+            g_s[g][jj] = g7[(int64_t)order[base + g] * 8 + jj];
         }
+        __syncthreads();
+        if (e < per_t)
+            for (int g = 0; g < cnt; ++g) accv = fmaf(c_s[g][k], g_s[g][j], accv);
+    }
+    if (e < per_t && accv != 0.f) {
+        atomicAdd(&dtable[(int64_t)t * per_t + e], -accv);
+        if (dbasis) atomicAdd(&dbasis[e], accv);
+    }
+}
+
+template <bool RAW, int DEG>
+static int launch_bwd(const PreBwdParams& p, int grid, size_t smem, cudaStream_t s) {
+    RDG_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<RAW, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    preprocess_bwd_kernel<RAW, DEG><<<grid, RDG_BLOCK, smem, s>>>(p);
+    RDG_CHECK_LAUNCH();
+    return RDG_OK;
+}
+
+template <bool RAW>
+static int launch_bwd_deg(const PreBwdParams& p, int deg, int grid, size_t smem, cudaStream_t s) {
+    switch (deg) {
+        case 0: return launch_bwd<RAW, 0>(p, grid, smem, s);
+        case 1: return launch_bwd<RAW, 1>(p, grid, smem, s);
+        case 2: return launch_bwd<RAW, 2>(p, grid, smem, s);
+        default: return launch_bwd<RAW, 3>(p, grid, smem, s);
     }
 }
 
@@ -392,33 +463,30 @@ extern "C" int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, co
     if (N == 0) return RDG_OK;
     RDG_CHECK_ARG(view->sh_degree >= 0 && view->sh_degree <= 3, "sh_degree must be 0..3");
     const bool deform = scene->raw && scene->use_deform && scene->n_dynamic > 0;
+    const bool csr = deform && scene->frame_order && scene->frame_offsets;
+    RDG_CHECK_ARG(!(csr && grads->table) || grads->g7_scratch, "g7_scratch is required with frame_order");
     PreBwdParams p;
     p.sc = *scene; p.view = *view; p.geom = *geom; p.gr = *grads; p.acc = acc;
-    // shared memory: dSH staging (45 KB) + the dL/dtable accumulators; the B(t)-table difference joins
-    // them only while two CTAs still fit per SM, otherwise it is read through L1.
-    size_t smem = RDG_BLOCK * SH_ROW * sizeof(float);
-    const size_t tab_bytes = deform ? (size_t)scene->num_times * scene->num_basis * 7 * sizeof(float) : 0;
-    p.dtab_in_smem = (deform && grads->table && smem + tab_bytes <= 200 * 1024) ? 1 : 0;
-    p.diff_in_smem = (deform && smem + (p.dtab_in_smem ? 2 : 1) * tab_bytes <= 100 * 1024) ? 1 : 0;
-    smem += (size_t)(p.dtab_in_smem + p.diff_in_smem) * tab_bytes;
-    if (deform && grads->table && !p.dtab_in_smem && grads->basis_t) {
-        rdg_set_error("rdg_preprocess_bwd: motion table with %d times does not fit in shared memory; "
-                      "pass basis_t = NULL and reduce dL/dtable on the host side", scene->num_times);
-        return RDG_E_ARG;
-    }
-    const int64_t chunks = (N + RDG_BLOCK - 1) / RDG_BLOCK;
-    const int per_sm = smem > 100 * 1024 ? 1 : 2;
-    const int64_t cap = (int64_t)RDG_SM_COUNT * per_sm * (deform ? 1 : 4);
+    if (!(csr && grads->table)) p.gr.g7_scratch = nullptr;
+    p.dtab_atomic = (deform && grads->table && !csr) ? 1 : 0;
+    const uintptr_t al = (uintptr_t)scene->st.sh_rest | (uintptr_t)scene->dy.sh_rest | (uintptr_t)grads->st.sh_rest |
+                         (uintptr_t)grads->dy.sh_rest;
+    p.use_tma = (al & 15u) == 0 ? 1 : 0;
+    const size_t smem = (RDG_BLOCK * SH_ROW + RDG_NUM_BASIS_MAX * 7) * sizeof(float);
+    const int64_t chunks = (scene->n_static + RDG_BLOCK - 1) / RDG_BLOCK + (scene->n_dynamic + RDG_BLOCK - 1) / RDG_BLOCK;
+    const int64_t cap = (int64_t)RDG_SM_COUNT * 2;   // 2 CTAs per SM (register-limited), persistent
     const int grid = (int)(chunks < cap ? chunks : cap);
     cudaStream_t s = (cudaStream_t)stream;
-    if (scene->raw) {
-        RDG_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        preprocess_bwd_kernel<true><<<grid, RDG_BLOCK, smem, s>>>(p);
-    } else {
-        RDG_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        preprocess_bwd_kernel<false><<<grid, RDG_BLOCK, smem, s>>>(p);
-    }
-    RDG_CHECK_LAUNCH();
+    const int rc = scene->raw ? launch_bwd_deg<true>(p, view->sh_degree, grid, smem, s)
+                              : launch_bwd_deg<false>(p, view->sh_degree, grid, smem, s);
+    if (rc) return rc;
     rdg_count_launches(1);
+    if (csr && grads->table) {
+        const dim3 g(scene->num_times, DT_SLICES);
+        dtable_kernel<<<g, 128, 0, s>>>(scene->frame_order, scene->frame_offsets, scene->motion_coeff, grads->g7_scratch,
+                                        scene->num_basis, grads->table, grads->basis_t);
+        RDG_CHECK_LAUNCH();
+        rdg_count_launches(1);
+    }
     return RDG_OK;
 }

@@ -4,13 +4,20 @@
 //
 // THIS TRANSLATION UNIT IS COMPILED WITH -fmad=false: depth bits, pixel centre,
 // radius and tile rectangle must be bit-identical to the oracle's individually
-// rounded float32 operations.  The kernel is HBM-bound (>= 236 B/Gaussian in,
-// 52 B out), so the lost FMA contraction costs nothing.
+// rounded float32 operations.  The kernel is HBM-bound, so the lost FMA contraction
+// costs nothing.
 //
 // Roofline: HBM.  Algorithmic bytes per Gaussian (degree 3): read 44 (xyz, scale,
 // quat, opacity) + 192 (SH) [+ 68 dynamic: coeff + birth index], write 8 (radii,
 // tiles_touched) + 41 for visible ones (p0, p1, p2, clamped).
+//
+// B200 mapping: one thread per Gaussian, 256-Gaussian chunks that never straddle the
+// static/dynamic boundary, so a chunk's higher-order SH rows are one contiguous,
+// 16-byte aligned 46 KB span: it is fetched by ONE cp.async.bulk (TMA) into shared memory
+// while the threads load their 44 B of geometry and run the projection; each thread then
+// reads its own row (stride 45 words: conflict-free).  46 KB per CTA -> 4 CTAs per SM.
 #include "scene.cuh"
+#include "tma.cuh"
 
 #define SH_ROW 45  // odd row stride in shared memory: conflict-free per-thread row reads
 
@@ -18,20 +25,18 @@ struct PreFwdParams {
     RdgScene sc;
     RdgView view;
     RdgGeom geom;
-    int diff_in_smem;   // stage D[t][k][j] = B(t) - table[t] in shared memory
-    int sh_in_smem;
+    int use_tma;
 };
 
-template <bool RAW>
+template <bool RAW, int DEG>
 __global__ void __launch_bounds__(RDG_BLOCK) preprocess_fwd_kernel(const PreFwdParams p) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(128) float smem[];
+    constexpr int K = (DEG + 1) * (DEG + 1);
+    constexpr int NREST = 3 * (K - 1);
     const RdgScene& sc = p.sc;
-    const int64_t N = sc.n_static + sc.n_dynamic;
-    const int deg = p.view.sh_degree;
-    const int K = (deg + 1) * (deg + 1);
-    const int nrest = 3 * (K - 1);
-    float* sh_s = smem;                                             // [256][SH_ROW]
-    float* diff_s = smem + (p.sh_in_smem ? RDG_BLOCK * SH_ROW : 0);  // [T][num_basis][7]
+    float* sh_s = smem;                       // [256][SH_ROW]
+    float* bt_s = smem + RDG_BLOCK * SH_ROW;  // [16*7] B(t)
+    __shared__ __align__(8) uint64_t bar;
 
     RdgCam cam;
     rdg_load_cam(cam, p.view.viewmatrix, p.view.projmatrix, p.view.tanfovx, p.view.tanfovy,
@@ -39,126 +44,140 @@ __global__ void __launch_bounds__(RDG_BLOCK) preprocess_fwd_kernel(const PreFwdP
     float campos[3];
     rdg_campos(cam, campos);
 
-    const float* diff = nullptr;
-    if (RAW && sc.use_deform && sc.n_dynamic > 0 && p.diff_in_smem) {
-        const int tot = sc.num_times * sc.num_basis * 7;
-        const int per_t = sc.num_basis * 7;
-        for (int e = threadIdx.x; e < tot; e += RDG_BLOCK) diff_s[e] = sc.basis_t[e % per_t] - sc.table[e];
-        diff = diff_s;
-    }
+    const bool deform = RAW && sc.use_deform && sc.n_dynamic > 0;
+    if (deform)
+        for (int e = threadIdx.x; e < sc.num_basis * 7; e += RDG_BLOCK) bt_s[e] = sc.basis_t[e];
+    if (threadIdx.x == 0) rdg_mbar_init(&bar, 1);
     __syncthreads();
 
-    const int64_t n_chunks = (N + RDG_BLOCK - 1) / RDG_BLOCK;
-    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        const int64_t base = chunk * RDG_BLOCK;
-        const int cnt = (int)min((int64_t)RDG_BLOCK, N - base);
-        const bool use_sh = (p.sc.colors_precomp == nullptr) && nrest > 0;
+    const bool use_sh = (sc.colors_precomp == nullptr) && NREST > 0;
+    const int64_t cs = (sc.n_static + RDG_BLOCK - 1) / RDG_BLOCK, cd = (sc.n_dynamic + RDG_BLOCK - 1) / RDG_BLOCK;
+    uint32_t phase = 0;
+    for (int64_t chunk = blockIdx.x; chunk < cs + cd; chunk += gridDim.x) {
+        const bool dyn = chunk >= cs;
+        const RdgSet& set = dyn ? sc.dy : sc.st;
+        const int64_t lbase = (dyn ? chunk - cs : chunk) * RDG_BLOCK;
+        const int64_t n_set = dyn ? sc.n_dynamic : sc.n_static;
+        const int cnt = (int)min((int64_t)RDG_BLOCK, n_set - lbase);
 
-        // ---- stage this chunk's higher-order SH rows in shared memory (coalesced) ----
-        if (use_sh && p.sh_in_smem) {
-            __syncthreads();  // previous chunk's readers are done
-            const bool one_set = (base >= sc.n_static) || (base + cnt <= sc.n_static);
-            const RdgSet& set0 = (base >= sc.n_static) ? sc.dy : sc.st;
-            if (one_set && set0.sh_rest_stride == nrest && nrest == SH_ROW) {
-                const int64_t lbase = (base >= sc.n_static) ? base - sc.n_static : base;
-                const float* src = set0.sh_rest + lbase * SH_ROW;
-                const int tot = cnt * SH_ROW;
-                for (int e = threadIdx.x; e < tot; e += RDG_BLOCK) sh_s[e] = src[e];
-            } else if (one_set && set0.sh_rest_stride == 48) {
-                // cat'ed [n,16,3] rows (the drop-in boundary): contiguous 192-byte rows, dc first
-                const int64_t lbase = (base >= sc.n_static) ? base - sc.n_static : base;
-                const float* src = set0.sh_rest + lbase * 48;
-                const int tot = cnt * 48 - 3;  // the pointer already skips the first row's dc
-                for (int e = threadIdx.x; e < tot; e += RDG_BLOCK) {
-                    const int g = e / 48, k = e - g * 48;
-                    if (k < nrest) sh_s[g * SH_ROW + k] = src[e];
+        // ---- stage this chunk's higher-order SH rows in shared memory ----
+        bool tma = false;
+        if (use_sh) {
+            __syncthreads();  // previous chunk's readers are done with sh_s
+            tma = p.use_tma && NREST == SH_ROW && set.sh_rest_stride == SH_ROW && (cnt & 3) == 0;
+            if (tma) {
+                if (threadIdx.x == 0) {
+                    rdg_fence_proxy_async();
+                    rdg_bulk_load(sh_s, set.sh_rest + lbase * SH_ROW, (uint32_t)(cnt * SH_ROW * sizeof(float)), &bar);
                 }
+            } else if (set.sh_rest_stride == NREST) {
+                const float* src = set.sh_rest + lbase * NREST;
+                for (int e = threadIdx.x; e < cnt * NREST; e += RDG_BLOCK) sh_s[(e / NREST) * SH_ROW + (e % NREST)] = src[e];
             } else {
-                const int tot = cnt * nrest;
-                for (int e = threadIdx.x; e < tot; e += RDG_BLOCK) {
-                    const int g = e / nrest, k = e - g * nrest;
-                    const int64_t gi = base + g;
-                    const bool dy = gi >= sc.n_static;
-                    const RdgSet& set = dy ? sc.dy : sc.st;
-                    const int64_t l = dy ? gi - sc.n_static : gi;
-                    sh_s[g * SH_ROW + k] = set.sh_rest[l * set.sh_rest_stride + k];
+                const int stride = set.sh_rest_stride;   // e.g. 48: cat'ed [n,16,3] rows of the drop-in boundary
+                const float* src = set.sh_rest + lbase * stride;
+                for (int e = threadIdx.x; e < cnt * NREST; e += RDG_BLOCK) {
+                    const int g = e / NREST, k = e - g * NREST;
+                    sh_s[g * SH_ROW + k] = src[(int64_t)g * stride + k];
                 }
             }
-            __syncthreads();
         }
 
-        const int64_t i = base + threadIdx.x;
-        if (i >= N) continue;
-
-        RdgAct a;
-        rdg_fetch<RAW>(sc, i, diff, a);
-        if (p.geom.dbg_activated) {
-            float* d = p.geom.dbg_activated + i * 11;
-            d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.s[0]; d[4] = a.s[1]; d[5] = a.s[2];
-            d[6] = a.q[0]; d[7] = a.q[1]; d[8] = a.q[2]; d[9] = a.q[3]; d[10] = a.op;
-        }
-
+        const bool valid = (int)threadIdx.x < cnt;
+        const int64_t local = lbase + threadIdx.x;
+        const int64_t i = (dyn ? sc.n_static : 0) + local;
         int radius = 0;
         unsigned tiles = 0;
-        // near-plane test needs only t.z, but the projection is cheap next to the loads
-        RdgProj pr;
-        rdg_project(cam, a, p.view.scale_modifier, pr);
-        if (pr.tz > RDG_NEAR_Z && pr.det != 0.0f) {
-            const float det_inv = 1.0f / pr.det;
-            const float conA = pr.cc * det_inv, conB = -pr.cb * det_inv, conC = pr.ca * det_inv;
-            const float mid = 0.5f * (pr.ca + pr.cc);
-            const float disc = sqrtf(fmaxf(0.1f, mid * mid - pr.det));
-            const float lam1 = mid + disc, lam2 = mid - disc;
-            const float rad_f = ceilf(3.0f * sqrtf(fmaxf(lam1, lam2)));
-            const float ndcx = pr.hx * pr.pw, ndcy = pr.hy * pr.pw;
-            const float px = ((ndcx + 1.0f) * cam.W - 1.0f) * 0.5f;
-            const float py = ((ndcy + 1.0f) * cam.H - 1.0f) * 0.5f;
-            const int rminx = min(cam.gx, max(0, (int)((px - rad_f) / 16.0f)));
-            const int rminy = min(cam.gy, max(0, (int)((py - rad_f) / 16.0f)));
-            const int rmaxx = min(cam.gx, max(0, (int)((px + rad_f + 15.0f) / 16.0f)));
-            const int rmaxy = min(cam.gy, max(0, (int)((py + rad_f + 15.0f) / 16.0f)));
-            const int cntt = (rmaxx - rminx) * (rmaxy - rminy);
-            if (cntt > 0) {
-                radius = (int)rad_f;
-                tiles = (unsigned)cntt;
-                float rgb[3];
-                unsigned clamped = 0;
-                if (sc.colors_precomp) {
-                    rgb[0] = sc.colors_precomp[i * 3 + 0];
-                    rgb[1] = sc.colors_precomp[i * 3 + 1];
-                    rgb[2] = sc.colors_precomp[i * 3 + 2];
-                } else {
-                    const RdgSet& set = a.dyn ? sc.dy : sc.st;
-                    const float* dc = set.sh_dc + a.local * set.sh_dc_stride;
-                    float dx = a.x - campos[0], dy = a.y - campos[1], dz = a.z - campos[2];
-                    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-                    dx *= inv; dy *= inv; dz *= inv;
-                    float b[16];
-                    rdg_sh_basis(deg, dx, dy, dz, b);
-                    rgb[0] = b[0] * dc[0]; rgb[1] = b[0] * dc[1]; rgb[2] = b[0] * dc[2];
-                    if (nrest > 0) {
-                        const float* rest = p.sh_in_smem ? (sh_s + threadIdx.x * SH_ROW)
-                                                         : (set.sh_rest + a.local * set.sh_rest_stride);
-                        for (int k = 1; k < K; ++k) {
-                            rgb[0] += b[k] * rest[(k - 1) * 3 + 0];
-                            rgb[1] += b[k] * rest[(k - 1) * 3 + 1];
-                            rgb[2] += b[k] * rest[(k - 1) * 3 + 2];
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        rgb[c] += 0.5f;
-                        if (rgb[c] < 0.0f) { clamped |= 1u << c; rgb[c] = 0.0f; }
-                    }
-                }
-                reinterpret_cast<float4*>(p.geom.p0)[i] = make_float4(px, py, conA, conB);
-                reinterpret_cast<float4*>(p.geom.p1)[i] = make_float4(conC, a.op, rgb[0], rgb[1]);
-                reinterpret_cast<float2*>(p.geom.p2)[i] = make_float2(rgb[2], pr.tz);
-                p.geom.clamped[i] = (uint8_t)clamped;
+        bool vis = false;
+        RdgAct a;
+        float px = 0.f, py = 0.f, conA = 0.f, conB = 0.f, conC = 0.f, tz = 0.f;
+        if (valid) {
+            rdg_fetch<RAW>(sc, dyn, local, bt_s, a);
+            if (p.geom.dbg_activated) {
+                float* d = p.geom.dbg_activated + i * 11;
+                d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.s[0]; d[4] = a.s[1]; d[5] = a.s[2];
+                d[6] = a.q[0]; d[7] = a.q[1]; d[8] = a.q[2]; d[9] = a.q[3]; d[10] = a.op;
+            }
+            RdgProj pr;
+            rdg_project(cam, a, p.view.scale_modifier, pr);
+            if (pr.tz > RDG_NEAR_Z && pr.det != 0.0f) {
+                const float det_inv = 1.0f / pr.det;
+                conA = pr.cc * det_inv; conB = -pr.cb * det_inv; conC = pr.ca * det_inv;
+                const float mid = 0.5f * (pr.ca + pr.cc);
+                const float disc = sqrtf(fmaxf(0.1f, mid * mid - pr.det));
+                const float lam1 = mid + disc, lam2 = mid - disc;
+                const float rad_f = ceilf(3.0f * sqrtf(fmaxf(lam1, lam2)));
+                const float ndcx = pr.hx * pr.pw, ndcy = pr.hy * pr.pw;
+                px = ((ndcx + 1.0f) * cam.W - 1.0f) * 0.5f;
+                py = ((ndcy + 1.0f) * cam.H - 1.0f) * 0.5f;
+                const int rminx = min(cam.gx, max(0, (int)((px - rad_f) / 16.0f)));
+                const int rminy = min(cam.gy, max(0, (int)((py - rad_f) / 16.0f)));
+                const int rmaxx = min(cam.gx, max(0, (int)((px + rad_f + 15.0f) / 16.0f)));
+                const int rmaxy = min(cam.gy, max(0, (int)((py + rad_f + 15.0f) / 16.0f)));
+                const int cntt = (rmaxx - rminx) * (rmaxy - rminy);
+                if (cntt > 0) { radius = (int)rad_f; tiles = (unsigned)cntt; vis = true; tz = pr.tz; }
             }
         }
-        p.geom.radii[i] = radius;
-        p.geom.tiles_touched[i] = tiles;
+        if (use_sh) {
+            if (tma) rdg_mbar_wait(&bar, phase & 1u);
+            else __syncthreads();
+        }
+        if (tma) ++phase;
+        if (vis) {
+            float rgb[3];
+            unsigned clamped = 0;
+            if (sc.colors_precomp) {
+                rgb[0] = sc.colors_precomp[i * 3 + 0];
+                rgb[1] = sc.colors_precomp[i * 3 + 1];
+                rgb[2] = sc.colors_precomp[i * 3 + 2];
+            } else {
+                const float* dc = set.sh_dc + local * set.sh_dc_stride;
+                float dx = a.x - campos[0], dy = a.y - campos[1], dz = a.z - campos[2];
+                const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+                dx *= inv; dy *= inv; dz *= inv;
+                float b[K];
+                rdg_sh_basis<DEG>(dx, dy, dz, b);
+                rgb[0] = b[0] * __ldg(dc); rgb[1] = b[0] * __ldg(dc + 1); rgb[2] = b[0] * __ldg(dc + 2);
+                const float* rest = sh_s + threadIdx.x * SH_ROW;
+#pragma unroll
+                for (int k = 1; k < K; ++k) {
+                    rgb[0] += b[k] * rest[(k - 1) * 3 + 0];
+                    rgb[1] += b[k] * rest[(k - 1) * 3 + 1];
+                    rgb[2] += b[k] * rest[(k - 1) * 3 + 2];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    rgb[c] += 0.5f;
+                    if (rgb[c] < 0.0f) { clamped |= 1u << c; rgb[c] = 0.0f; }
+                }
+            }
+            reinterpret_cast<float4*>(p.geom.p0)[i] = make_float4(px, py, conA, conB);
+            reinterpret_cast<float4*>(p.geom.p1)[i] = make_float4(conC, a.op, rgb[0], rgb[1]);
+            reinterpret_cast<float2*>(p.geom.p2)[i] = make_float2(rgb[2], tz);
+            p.geom.clamped[i] = (uint8_t)clamped;
+        }
+        if (valid) {
+            p.geom.radii[i] = radius;
+            p.geom.tiles_touched[i] = tiles;
+        }
+    }
+}
+
+template <bool RAW, int DEG>
+static int launch_fwd(const PreFwdParams& p, int grid, size_t smem, cudaStream_t s) {
+    RDG_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<RAW, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    preprocess_fwd_kernel<RAW, DEG><<<grid, RDG_BLOCK, smem, s>>>(p);
+    RDG_CHECK_LAUNCH();
+    return RDG_OK;
+}
+
+template <bool RAW>
+static int launch_fwd_deg(const PreFwdParams& p, int deg, int grid, size_t smem, cudaStream_t s) {
+    switch (deg) {
+        case 0: return launch_fwd<RAW, 0>(p, grid, smem, s);
+        case 1: return launch_fwd<RAW, 1>(p, grid, smem, s);
+        case 2: return launch_fwd<RAW, 2>(p, grid, smem, s);
+        default: return launch_fwd<RAW, 3>(p, grid, smem, s);
     }
 }
 
@@ -178,6 +197,9 @@ extern "C" int rdg_preprocess_fwd(const RdgScene* scene, const RdgView* view, co
                   "null dynamic parameter");
     RDG_CHECK_ARG(scene->colors_precomp || ((scene->n_static == 0 || scene->st.sh_dc) && (scene->n_dynamic == 0 || scene->dy.sh_dc)),
                   "exactly one of SHs / precomputed colours is required");
+    RDG_CHECK_ARG(scene->colors_precomp || view->sh_degree == 0 ||
+                      ((scene->n_static == 0 || scene->st.sh_rest) && (scene->n_dynamic == 0 || scene->dy.sh_rest)),
+                  "null higher-order SH pointer");
     const bool deform = scene->raw && scene->use_deform && scene->n_dynamic > 0;
     if (deform) {
         RDG_CHECK_ARG(scene->num_basis > 0 && scene->num_basis <= RDG_NUM_BASIS_MAX, "num_basis out of range");
@@ -188,24 +210,17 @@ extern "C" int rdg_preprocess_fwd(const RdgScene* scene, const RdgView* view, co
     p.sc = *scene;
     p.view = *view;
     p.geom = *geom;
-    const bool need_sh = scene->colors_precomp == nullptr && view->sh_degree > 0;
-    p.sh_in_smem = need_sh ? 1 : 0;
-    size_t smem = p.sh_in_smem ? RDG_BLOCK * SH_ROW * sizeof(float) : 0;
-    const size_t diff_bytes = deform ? (size_t)scene->num_times * scene->num_basis * 7 * sizeof(float) : 0;
-    p.diff_in_smem = (deform && smem + diff_bytes <= 160 * 1024) ? 1 : 0;
-    if (p.diff_in_smem) smem += diff_bytes;
-    const int64_t chunks = (N + RDG_BLOCK - 1) / RDG_BLOCK;
-    // persistent-ish grid: a multiple of the SM count so the staged table is amortised
+    // TMA needs 16-byte aligned global sources; torch allocations are, arbitrary views may not be
+    const bool aligned = (((uintptr_t)scene->st.sh_rest | (uintptr_t)scene->dy.sh_rest) & 15u) == 0;
+    p.use_tma = aligned ? 1 : 0;
+    const size_t smem = (RDG_BLOCK * SH_ROW + RDG_NUM_BASIS_MAX * 7) * sizeof(float);
+    const int64_t chunks = (scene->n_static + RDG_BLOCK - 1) / RDG_BLOCK + (scene->n_dynamic + RDG_BLOCK - 1) / RDG_BLOCK;
+    // persistent grid: a multiple of the SM count (4 CTAs of 46 KB fit per SM)
     const int grid = (int)(chunks < (int64_t)RDG_SM_COUNT * 4 ? chunks : (int64_t)RDG_SM_COUNT * 4);
     cudaStream_t s = (cudaStream_t)stream;
-    if (scene->raw) {
-        RDG_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        preprocess_fwd_kernel<true><<<grid, RDG_BLOCK, smem, s>>>(p);
-    } else {
-        RDG_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        preprocess_fwd_kernel<false><<<grid, RDG_BLOCK, smem, s>>>(p);
-    }
-    RDG_CHECK_LAUNCH();
+    const int rc = scene->raw ? launch_fwd_deg<true>(p, view->sh_degree, grid, smem, s)
+                              : launch_fwd_deg<false>(p, view->sh_degree, grid, smem, s);
+    if (rc) return rc;
     rdg_count_launches(1);
     return RDG_OK;
 }

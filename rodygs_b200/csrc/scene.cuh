@@ -23,44 +23,73 @@ struct RdgAct {
     int64_t local;     // index inside its own set
 };
 
-// Motion-basis difference D[t][k][j] = B(t)[k][j] - table[t][k][j]; `diff` may
-// live in shared memory (staged per block) or be null, in which case it is
-// formed on the fly from global memory.
-__device__ __forceinline__ float rdg_basis_diff(const RdgScene& sc, const float* diff, int ti, int k, int j) {
-    if (diff) return diff[(ti * sc.num_basis + k) * 7 + j];
-    return sc.basis_t[k * 7 + j] - sc.table[((int64_t)ti * sc.num_basis + k) * 7 + j];
+// B(t)[k][j] - table[ti][k][j].  B(t) is 112 floats that every thread reads at the same
+// address (broadcast from shared memory or L1); the table row of the Gaussian's birth frame
+// (448 B, 16-byte aligned) is read with vector loads and stays L1/L2 resident (T rows, 45 KB).
+__device__ __forceinline__ float rdg_basis_diff(const RdgScene& sc, const float* basis_t, int ti, int k, int j) {
+    return basis_t[k * 7 + j] - __ldg(sc.table + ((int64_t)ti * sc.num_basis + k) * 7 + j);
+}
+
+// delta[j] = sum_k c_k (B(t)[k][j] - table[ti][k][j]),  j = 0..6
+__device__ __forceinline__ void rdg_deform_delta(const RdgScene& sc, const float* basis_t, int ti, const float* c, float* d) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j) d[j] = 0.f;
+    const float* row = sc.table + (int64_t)ti * sc.num_basis * 7;
+    if (sc.num_basis == RDG_NUM_BASIS_MAX) {
+        const float4* row4 = reinterpret_cast<const float4*>(row);   // 112 floats = 28 float4
+#pragma unroll
+        for (int q = 0; q < 28; ++q) {
+            const float4 v = __ldg(row4 + q);
+            const float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int e = 4 * q + m;          // e = k*7 + j, compile-time after unrolling
+                d[e % 7] += c[e / 7] * (basis_t[e] - r[m]);
+            }
+        }
+    } else {
+        for (int k = 0; k < sc.num_basis; ++k)
+#pragma unroll
+            for (int j = 0; j < 7; ++j) d[j] += c[k] * (basis_t[k * 7 + j] - __ldg(row + k * 7 + j));
+    }
 }
 
 template <bool RAW>
-__device__ __forceinline__ void rdg_fetch(const RdgScene& sc, int64_t i, const float* diff, RdgAct& a) {
-    a.dyn = i >= sc.n_static;
-    a.local = a.dyn ? i - sc.n_static : i;
-    const RdgSet& set = a.dyn ? sc.dy : sc.st;
-    const float* px = set.xyz + a.local * 3;
-    const float* ps = set.scaling + a.local * 3;
-    const float* pq = set.rotation + a.local * 4;
-    a.x = px[0]; a.y = px[1]; a.z = px[2];
-    float s0 = ps[0], s1 = ps[1], s2 = ps[2];
-    float q0 = pq[0], q1 = pq[1], q2 = pq[2], q3 = pq[3];
-    float o = set.opacity[a.local];
+__device__ __forceinline__ void rdg_fetch(const RdgScene& sc, bool dyn, int64_t local, const float* basis_t, RdgAct& a) {
+    a.dyn = dyn;
+    a.local = local;
+    const RdgSet& set = dyn ? sc.dy : sc.st;
+    const float* px = set.xyz + local * 3;
+    const float* ps = set.scaling + local * 3;
+    const float4 q4 = __ldg(reinterpret_cast<const float4*>(set.rotation) + local);
+    a.x = __ldg(px); a.y = __ldg(px + 1); a.z = __ldg(px + 2);
+    const float s0 = __ldg(ps), s1 = __ldg(ps + 1), s2 = __ldg(ps + 2);
+    const float q0 = q4.x, q1 = q4.y, q2 = q4.z, q3 = q4.w;
+    const float o = __ldg(set.opacity + local);
     a.ti = 0;
     if (RAW) {
         a.s[0] = expf(s0); a.s[1] = expf(s1); a.s[2] = expf(s2);
-        float nrm = sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+        const float nrm = sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
         a.qinv = 1.0f / fmaxf(nrm, 1e-12f);
         a.qn[0] = q0 * a.qinv; a.qn[1] = q1 * a.qinv; a.qn[2] = q2 * a.qinv; a.qn[3] = q3 * a.qinv;
         a.q[0] = a.qn[0]; a.q[1] = a.qn[1]; a.q[2] = a.qn[2]; a.q[3] = a.qn[3];
         a.op = 1.0f / (1.0f + expf(-o));
-        if (a.dyn && sc.use_deform) {
-            const float* pc = sc.motion_coeff + a.local * sc.num_basis;
-            a.ti = sc.time_ind[a.local];
-            float d[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int k = 0; k < sc.num_basis; ++k) {
-                float ck = pc[k];
-                a.c[k] = ck;
+        if (dyn && sc.use_deform) {
+            const float* pc = sc.motion_coeff + local * sc.num_basis;
+            a.ti = __ldg(sc.time_ind + local);
+            if (sc.num_basis == RDG_NUM_BASIS_MAX) {
+                const float4* pc4 = reinterpret_cast<const float4*>(pc);
 #pragma unroll
-                for (int j = 0; j < 7; ++j) d[j] += ck * rdg_basis_diff(sc, diff, a.ti, k, j);
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = __ldg(pc4 + q);
+                    a.c[4 * q] = v.x; a.c[4 * q + 1] = v.y; a.c[4 * q + 2] = v.z; a.c[4 * q + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < RDG_NUM_BASIS_MAX; ++k) a.c[k] = k < sc.num_basis ? __ldg(pc + k) : 0.f;
             }
+            float d[7];
+            rdg_deform_delta(sc, basis_t, a.ti, a.c, d);
             a.x += d[0] * sc.spatial_lr_scale;
             a.y += d[1] * sc.spatial_lr_scale;
             a.z += d[2] * sc.spatial_lr_scale;
@@ -157,7 +186,8 @@ __device__ __forceinline__ void rdg_project(const RdgCam& cam, const RdgAct& a, 
 }
 
 // SH basis values for a unit direction (sh_utils.py:72-101), b[0..K-1].
-__device__ __forceinline__ void rdg_sh_basis(int deg, float x, float y, float z, float* b) {
+template <int deg>
+__device__ __forceinline__ void rdg_sh_basis(float x, float y, float z, float* b) {
     b[0] = RDG_SH_C0;
     if (deg > 0) {
         b[1] = -RDG_SH_C1 * y;

@@ -106,6 +106,8 @@ class SceneArgs:
     basis_t: Optional[torch.Tensor] = None        # [K,7]
     table: Optional[torch.Tensor] = None          # [T,K,7]
     spatial_lr_scale: float = 1.0
+    frame_order: Optional[torch.Tensor] = None    # [nd] int32, stable argsort(time_ind)
+    frame_offsets: Optional[torch.Tensor] = None  # [T+1] int32
 
     def counts(self):
         ns = self.st.n() if self.st is not None else 0
@@ -175,6 +177,8 @@ def _scene_struct(sc: SceneArgs) -> RdgScene:
         out.time_ind = ptr(sc.time_ind)
         out.basis_t = ptr(sc.basis_t)
         out.table = ptr(sc.table)
+        out.frame_order = ptr(sc.frame_order)
+        out.frame_offsets = ptr(sc.frame_offsets)
     out.spatial_lr_scale = float(sc.spatial_lr_scale)
     return out
 
@@ -200,6 +204,26 @@ def _geom_struct(g: dict) -> RdgGeom:
     out.p0, out.p1, out.p2 = ptr(g["p0"]), ptr(g["p1"]), ptr(g["p2"])
     out.clamped = ptr(g["clamped"])
     out.dbg_activated = ptr(g.get("dbg_activated"))
+    return out
+
+
+_csr_cache: Dict[tuple, tuple] = {}
+
+
+def frame_csr(time_ind: torch.Tensor, num_times: int):
+    """CSR of the dynamic Gaussians by birth frame: (order [nd] int32, offsets [T+1] int32).
+    Built on the device once per `time_ind` tensor (it only changes on densification) and cached."""
+    key = (time_ind.data_ptr(), time_ind._version, time_ind.numel(), int(num_times), time_ind.device.index)
+    hit = _csr_cache.get(key)
+    if hit is not None:
+        return hit
+    if len(_csr_cache) > 16:
+        _csr_cache.clear()
+    ti = time_ind.long()
+    sorted_ti, order = torch.sort(ti, stable=True)
+    offsets = torch.searchsorted(sorted_ti, torch.arange(num_times + 1, device=ti.device))
+    out = (order.to(torch.int32).contiguous(), offsets.to(torch.int32).contiguous())
+    _csr_cache[key] = out
     return out
 
 
@@ -306,6 +330,7 @@ class SceneGrads:
     motion_coeff: Optional[torch.Tensor] = None
     table: Optional[torch.Tensor] = None        # must be zero-initialised
     basis_t: Optional[torch.Tensor] = None      # must be zero-initialised
+    g7_scratch: Optional[torch.Tensor] = None   # [nd,8] scratch (allocated on demand)
 
 
 def _setgrad_struct(g: SetGrads) -> RdgSetGrad:
@@ -341,6 +366,10 @@ def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: Sce
     g.st, g.dy = _setgrad_struct(grads.st), _setgrad_struct(grads.dy)
     g.colors_precomp, g.means2D, g.viewmatrix = ptr(grads.colors_precomp), ptr(grads.means2D), ptr(grads.viewmatrix)
     g.motion_coeff, g.table, g.basis_t = ptr(grads.motion_coeff), ptr(grads.table), ptr(grads.basis_t)
+    if state.scene.use_deform and state.scene.frame_order is not None and grads.table is not None:
+        if grads.g7_scratch is None:
+            grads.g7_scratch = torch.empty(state.scene.motion_coeff.shape[0], 8, dtype=torch.float32, device=dev)
+        g.g7_scratch = ptr(grads.g7_scratch)
     check(lib.rdg_preprocess_bwd(C.byref(sc_s), C.byref(vw_s), C.byref(gm_s), ptr(acc), C.byref(g), stream))
     if stage_hook:
         stage_hook("preprocess_bwd")

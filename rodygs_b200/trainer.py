@@ -82,6 +82,8 @@ class SplatTrainStep:
         self.p("table").copy_(scene["table"])
         self.time_ind = scene["time_ind"].to(self.dev, torch.int32).contiguous()
         self.spatial_lr_scale = float(scene["spatial_lr_scale"])
+        self.frame_order, self.frame_offsets = engine.frame_csr(self.time_ind, self.T) if nd > 0 else (None, None)
+        self._g7 = torch.empty(max(nd, 1), 8, dtype=torch.float32, device=self.dev)
         self.bg = torch.zeros(3, dtype=torch.float32, device=self.dev)          # rodygs.py:267
         n = ns + nd
         f32 = dict(dtype=torch.float32, device=self.dev)
@@ -152,7 +154,8 @@ class SplatTrainStep:
         scene = SceneArgs(st=self._set("static"), dy=self._set("dynamic"), raw=True, use_deform=deform,
                           motion_coeff=self.p("motion_coeff").view(self.nd, self.num_basis) if deform else None,
                           time_ind=self.time_ind if deform else None, basis_t=basis_t if deform else None,
-                          table=self.p("table") if deform else None, spatial_lr_scale=self.spatial_lr_scale)
+                          table=self.p("table") if deform else None, spatial_lr_scale=self.spatial_lr_scale,
+                          frame_order=self.frame_order, frame_offsets=self.frame_offsets)
         view = ViewArgs(height=self.H, width=self.W, tanfovx=tanfovx, tanfovy=tanfovy, scale_modifier=1.0,
                         sh_degree=self.sh_degree, viewmatrix=viewmatrix, projmatrix=projmatrix, bg=self.bg)
         self._mark("start")
@@ -190,7 +193,8 @@ class SplatTrainStep:
             grads = SceneGrads(st=self._setgrad("static"), dy=self._setgrad("dynamic"), means2D=self.means2D_grad,
                                viewmatrix=self.view_grad,
                                motion_coeff=self.g("motion_coeff").view(self.nd, self.num_basis) if deform else None,
-                               table=self.g("table") if deform else None, basis_t=self.g("basis_t") if deform else None)
+                               table=self.g("table") if deform else None, basis_t=self.g("basis_t") if deform else None,
+                               g7_scratch=self._g7)
             engine.render_backward(state, self.dL_dcolor, self.dL_ddepth if use_depth else None,
                                    self.dL_dalpha if use_alpha else None, grads, stage_hook=self._mark)
         finally:
