@@ -238,9 +238,11 @@ __global__ void __launch_bounds__(BATCH) blend_bwd_kernel(const uint2* __restric
     max_last = min(max_last, (uint32_t)n_g);
     if (max_last == 0) return;
 
+    // Running state per pixel.  With P_i = <g, (r,g,b,depth,1)_i> the alpha gradient is
+    //   dL/dalpha_i = T_i P_i - (A_dot_i + T_final <g_rgb, bg>) / (1 - alpha_i),  A_dot_i = sum_{k>i} P_k alpha_k T_k,
+    // so one scalar recursion replaces the five per-channel "accumulated behind" recursions.
     float T = T_final;
-    float rec_r = 0.f, rec_g = 0.f, rec_b = 0.f, rec_d = 0.f, rec_a = 0.f;
-    float last_alpha = 0.f, last_r = 0.f, last_g = 0.f, last_b = 0.f, last_d = 0.f;
+    float A_dot = T_final * bg_dot;
     const int own_k = rdg_rs10_index(lane);
 
     const int rounds = ((int)max_last + BATCH - 1) / BATCH;
@@ -279,27 +281,19 @@ __global__ void __launch_bounds__(BATCH) blend_bwd_kernel(const uint2* __restric
                 for (int k = 0; k < 10; ++k) v[k] = 0.f;
                 if (on) {
                     const float2 c = sm.c[j];
-                    T = T / (1.0f - alpha);
+                    const float inv = __fdividef(1.0f, 1.0f - alpha);
+                    T *= inv;                                     // transmittance in front of this Gaussian
                     const float wgt = alpha * T;
-                    const float om = 1.f - last_alpha;
-                    rec_r = last_alpha * last_r + om * rec_r;
-                    rec_g = last_alpha * last_g + om * rec_g;
-                    rec_b = last_alpha * last_b + om * rec_b;
-                    rec_d = last_alpha * last_d + om * rec_d;
-                    rec_a = last_alpha + om * rec_a;
-                    last_r = b.z; last_g = b.w; last_b = c.x; last_d = c.y;
-                    float dL_da = (b.z - rec_r) * gr + (b.w - rec_g) * gg + (c.x - rec_b) * gb + (c.y - rec_d) * gd + (1.f - rec_a) * ga;
-                    dL_da *= T;
-                    last_alpha = alpha;
-                    dL_da += (-T_final / (1.f - alpha)) * bg_dot;
-                    const float dL_dG = b.y * dL_da;
-                    const float gdx = G * dx, gdy = G * dy;
-                    v[0] = dL_dG * (-gdx * a.z - gdy * a.w);      // d/dpx (pixel units)
-                    v[1] = dL_dG * (-gdy * b.x - gdx * a.w);      // d/dpy
-                    v[2] = -0.5f * gdx * dx * dL_dG;              // dA
-                    v[3] = -gdx * dy * dL_dG;                     // dB (B enters `power` once)
-                    v[4] = -0.5f * gdy * dy * dL_dG;              // dC
-                    v[5] = G * dL_da;                             // dopacity
+                    const float P = fmaf(b.z, gr, fmaf(b.w, gg, fmaf(c.x, gb, fmaf(c.y, gd, ga))));
+                    const float dL_da = fmaf(T, P, -inv * A_dot);
+                    A_dot = fmaf(P, wgt, A_dot);
+                    // raw moments; the conic / sign factors are applied once per (Gaussian, tile) at the flush
+                    const float t5 = G * dL_da;                   // d/dopacity
+                    const float w = b.y * t5;                     // dL/dG * G
+                    const float wx = w * dx, wy = w * dy;
+                    v[0] = wx; v[1] = wy;
+                    v[2] = wx * dx; v[3] = wx * dy; v[4] = wy * dy;
+                    v[5] = t5;
                     v[6] = wgt * gr; v[7] = wgt * gg; v[8] = wgt * gb;   // drgb
                     v[9] = wgt * gd;                              // ddepth
                 }
@@ -310,10 +304,19 @@ __global__ void __launch_bounds__(BATCH) blend_bwd_kernel(const uint2* __restric
         __syncthreads();
         if ((int)threadIdx.x < cnt) {
             float4* row = reinterpret_cast<float4*>(&sacc[threadIdx.x][0]);
-            const float4 r0 = row[0], r1 = row[1], r2 = row[2];
+            float4 r0 = row[0], r1 = row[1], r2 = row[2];
             const bool nz = r0.x != 0.f || r0.y != 0.f || r0.z != 0.f || r0.w != 0.f || r1.x != 0.f || r1.y != 0.f ||
                             r1.z != 0.f || r1.w != 0.f || r2.x != 0.f || r2.y != 0.f;
             if (nz) {
+                // moments -> gradients: dpx = -(A Sx + B Sy), dpy = -(C Sy + B Sx), dA = -Sxx/2, dB = -Sxy, dC = -Syy/2
+                const float4 ga4 = sm.a[threadIdx.x];
+                const float cA = ga4.z, cB = ga4.w, cC = sm.b[threadIdx.x].x;
+                const float sx = r0.x, sy = r0.y;
+                r0.x = -(cA * sx + cB * sy);
+                r0.y = -(cC * sy + cB * sx);
+                r0.z *= -0.5f;
+                r0.w = -r0.w;
+                r1.x *= -0.5f;
                 float4* dst = reinterpret_cast<float4*>(acc + (size_t)sm.id[threadIdx.x] * NACC);
                 atomicAdd(dst + 0, r0);
                 atomicAdd(dst + 1, r1);
