@@ -52,6 +52,18 @@ def shard_views(n_views: int, world_size: int, rank: int) -> List[int]:
     return [v for v in range(n_views) if v % world_size == rank]
 
 
+def allreduce_flat(buf: torch.Tensor, scale: Optional[float] = None, group=None) -> torch.Tensor:
+    """The data path's only exchange step: in-place sum of the flat gradient buffer over the
+    data-parallel group (NCCL on GPUs, gloo in the CPU tests), then an optional scale
+    (1 / views for a mean over the step's views)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    if scale is not None and scale != 1.0:
+        buf.mul_(scale)
+    return buf
+
+
 class SplatTrainStep:
     """Holds the flat parameter and gradient buffers of a static + dynamic model and runs
     forward + losses + backward for one view.
@@ -205,11 +217,7 @@ class SplatTrainStep:
 
     def allreduce_grads(self, scale: Optional[float] = None):
         """Sum (and optionally scale) the flat gradient buffer over the data-parallel group."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1:
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.pg)
-        if scale is not None and scale != 1.0:
-            self.grads.mul_(scale)
+        allreduce_flat(self.grads, scale, self.pg)
 
     def total_loss(self) -> torch.Tensor:
         """photometric + w_p * pearson + alpha term (device scalar)."""

@@ -1,0 +1,139 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol the header declares,
+argument errors are reported without touching a GPU, and the host-side mirror of the
+reference interface behaves like the reference's (names, fields, error behaviour)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "rodygs_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rdg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rodygs_b200 import _lib
+    lib = _lib.load()
+    declared = _header_symbols()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/rodygs_b200.h but not exported"
+        assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype in rodygs_b200/_lib.py"
+    assert set(_lib.SYMBOLS) == set(declared)
+    assert lib.rdg_abi_version() == 2
+    assert isinstance(lib.rdg_launch_count(), int)
+
+
+def test_struct_layouts_match_header_sizes():
+    """ctypes mirrors must have the C layout (pointer = 8 bytes, natural alignment)."""
+    from rodygs_b200 import _lib
+    assert C.sizeof(_lib.RdgSet) == 6 * 8 + 2 * 4
+    assert C.sizeof(_lib.RdgView) == 2 * 4 + 3 * 4 + 3 * 4 + 3 * 8
+    assert C.sizeof(_lib.RdgGeom) == 7 * 8
+    assert C.sizeof(_lib.RdgBins) == 7 * 8
+    assert C.sizeof(_lib.RdgImage) == 5 * 8
+    assert C.sizeof(_lib.RdgSetGrad) == 6 * 8
+    assert C.sizeof(_lib.RdgSceneGrad) == 2 * 48 + 7 * 8
+    assert C.sizeof(_lib.RdgScene) == 16 + 2 * 56 + 8 + 8 + 16 + 4 * 8 + 8 + 2 * 8
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from rodygs_b200 import _lib
+    lib = _lib.load()
+    assert lib.rdg_preprocess_fwd(None, None, None, None) == -1
+    assert b"null argument" in lib.rdg_last_error()
+    view = _lib.RdgView()
+    view.height, view.width, view.sh_degree = 16, 16, 7
+    scene, geom = _lib.RdgScene(), _lib.RdgGeom()
+    scene.n_static = 4
+    assert lib.rdg_preprocess_fwd(C.byref(scene), C.byref(view), C.byref(geom), None) == -1
+    assert b"sh_degree" in lib.rdg_last_error()
+    assert lib.rdg_bin_workspace_bytes(-1, 10, 16, 16) == -1
+    ws = lib.rdg_bin_workspace_bytes(1000, 4000, 64, 64)
+    assert ws > 4000 * 12 and ws % 256 == 0
+    assert lib.rdg_l1_dssim_workspace_bytes(3, 0, 10) == -1
+    assert lib.rdg_l1_dssim_workspace_bytes(3, 8, 8) == 256 + 3 * 3 * 64 * 4
+    assert lib.rdg_adam(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-15, 1, 1.0, None) == -1
+    with pytest.raises(RuntimeError, match="rodygs_b200 error -1"):
+        _lib.check(lib.rdg_blend_fwd(0, None, None, None, None, None))
+
+
+def test_settings_and_rasterizer_mirror_the_reference_interface():
+    import diff_gauss_pose
+    from rodygs_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    assert diff_gauss_pose.GaussianRasterizer is GaussianRasterizer
+    # exactly the 12 keyword fields of /root/reference/src/trainer/renderer.py:50-63, in order
+    assert GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "projmatrix", "sh_degree",
+        "prefiltered", "debug", "enable_cov_grad", "enable_sh_grad")
+    st = GaussianRasterizationSettings(image_height=8, image_width=8, tanfovx=0.5, tanfovy=0.5, bg=torch.zeros(3),
+                                       scale_modifier=1.0, projmatrix=torch.eye(4), sh_degree=0, prefiltered=False,
+                                       debug=False, enable_cov_grad=True, enable_sh_grad=True)
+    rast = GaussianRasterizer(raster_settings=st)
+    n = 4
+    kw = dict(means3D=torch.zeros(n, 3), means2D=torch.zeros(n, 3), shs=torch.zeros(n, 16, 3), colors_precomp=None,
+              opacities=torch.zeros(n, 1), scales=torch.ones(n, 3), rotations=torch.ones(n, 4), cov3Ds_precomp=None,
+              viewmatrix=torch.eye(4))
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        rast(**{**kw, "shs": None})
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        rast(**{**kw, "colors_precomp": torch.zeros(n, 3)})
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        rast(**{**kw, "rotations": None})
+    with pytest.raises(NotImplementedError):
+        rast(**{**kw, "scales": None, "rotations": None, "cov3Ds_precomp": torch.zeros(n, 6)})
+    # the product path refuses CPU tensors instead of silently falling back
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rast(**kw)
+
+
+def test_product_path_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under rodygs_b200/ (or the shim) may reference it."""
+    for base in ("rodygs_b200", "diff_gauss_pose"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from rodygs_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.load()
+
+
+def test_flat_layout_and_view_sharding():
+    from rodygs_b200.trainer import flat_layout, shard_views
+    layout, total = flat_layout(1000, 500, 16, 10)
+    offs = sorted((o, n) for n, (o, _) in layout.items())
+    assert all(o % 64 == 0 for o, _ in offs)
+    assert layout["static.features_rest"][1] == (1000, 15, 3) and layout["table"][1] == (10, 16, 7)
+    ends = []
+    for name, (o, shp) in layout.items():
+        numel = 1
+        for s in shp:
+            numel *= s
+        ends.append((o, o + numel))
+    ends.sort()
+    assert all(a[1] <= b[0] for a, b in zip(ends, ends[1:])), "slices overlap"
+    assert ends[-1][1] <= total
+    for world in (1, 2, 4, 8):
+        got = sorted(v for r in range(world) for v in shard_views(8, world, r))
+        assert got == list(range(8))
+        assert all(len(shard_views(8, world, r)) == 8 // world for r in range(world))
+
+
+def test_algorithmic_bytes_formula_matches_baseline_md():
+    from rodygs_b200.synthetic import algorithmic_bytes
+    # BASELINE.md §3.3 worked examples
+    assert abs(algorithmic_bytes(2_000_000, 2_000_000, 1_000_000, 8_000_000, 2_073_600) / 1e9 - 3.34) < 0.03
+    assert abs(algorithmic_bytes(6_000_000, 6_000_000, 3_000_000, 24_000_000, 2_073_600, forward_only=True) / 1e9 - 4.25) < 0.03

@@ -1,0 +1,86 @@
+"""World-size-2 test of the view-sharded data-parallel step on CPU (gloo stands in for NCCL):
+two ranks each take their round-robin share of a step's views, write per-view gradients of
+every parameter into the flat buffer layout the CUDA trainer uses, and all-reduce it; the result
+must equal the single-process sum over all views.  The per-view gradients come from the oracle
+(the CUDA engine cannot run here), so this covers exactly the host logic of the N>1 path:
+shard_views, flat_layout and allreduce_flat."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import helpers
+from oracle import deform_oracle as do
+from oracle import loss_oracle as lo
+from oracle import splat_oracle as so
+from rodygs_b200 import synthetic
+from rodygs_b200.trainer import PARAM_ORDER, allreduce_flat, flat_layout, shard_views
+
+N, H, W, T, VIEWS = 600, 48, 64, 4, 4
+
+
+def _view_grads(sc, view, layout, total):
+    cam = synthetic.make_camera(view, VIEWS, H, W, T)
+    leaf = lambda t: t.detach().clone().requires_grad_(True)
+    st = do.RawGaussians(**{k: leaf(v) for k, v in sc["static"].items()})
+    dy = do.RawGaussians(**{k: leaf(v) for k, v in sc["dynamic"].items()})
+    coeff, table = leaf(sc["motion_coeff"]), leaf(sc["table"])
+    basis_t = leaf(sc["table"][cam.time_index])
+    xyz, op, scl, rot, feat = do.assemble(st, dy, coeff.squeeze(1), basis_t, table, sc["time_ind"].long(), 1.0, True)
+    out = so.rasterize(xyz, None, feat, None, op, scl, rot, cam.world_view_transform.t().contiguous(),
+                       helpers.oracle_settings(cam, torch.zeros(3), 3))
+    gt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(1000 + view))
+    lo.photometric(out.color, gt).backward()
+    flat = torch.zeros(total)
+    def put(name, t):
+        off, shp = layout[name]
+        g = t.grad if t.grad is not None else torch.zeros_like(t)
+        flat[off:off + g.numel()] = g.reshape(-1)
+    for tag, model in (("static", st), ("dynamic", dy)):
+        for k in PARAM_ORDER:
+            put(f"{tag}.{k}", getattr(model, k))
+    put("motion_coeff", coeff); put("table", table); put("basis_t", basis_t)
+    return flat
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sc = synthetic.make_scene(N, H, W, T, seed=3)
+        layout, total = flat_layout(sc["static"]["xyz"].shape[0], sc["dynamic"]["xyz"].shape[0], 16, T)
+        flat = torch.zeros(total)
+        for v in shard_views(VIEWS, world, rank):
+            flat += _view_grads(sc, v, layout, total)
+        allreduce_flat(flat, 1.0 / VIEWS)
+        if rank == 0:
+            ret.put(flat.clone())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_view_sharded_allreduce_matches_sequential():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = ret.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sc = synthetic.make_scene(N, H, W, T, seed=3)
+    layout, total = flat_layout(sc["static"]["xyz"].shape[0], sc["dynamic"]["xyz"].shape[0], 16, T)
+    ref = torch.zeros(total)
+    for v in range(VIEWS):
+        ref += _view_grads(sc, v, layout, total)
+    ref /= VIEWS
+    assert ref.abs().max() > 0
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-8)
