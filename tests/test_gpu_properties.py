@@ -1,0 +1,154 @@
+"""Size-independent properties of the CUDA path at BASELINE.json's full sizes (where the
+CPU oracle would take hours): sortedness, consistency of the binning tables, conservation
+identities, determinism of the forward pass and linearity of the backward pass."""
+import pytest
+import torch
+
+from rodygs_b200 import engine, synthetic
+from rodygs_b200.trainer import SplatTrainStep
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _reset():
+    yield
+    engine.config.sync_free = False
+    engine.config.debug_keep_unsorted = False
+
+
+def _step(cfg, n_override=None):
+    N, H, W, T, _ = synthetic.CONFIGS[cfg]
+    if n_override:
+        N = n_override
+    scene = synthetic.to_device(synthetic.make_scene(N, H, W, T, seed=0), "cuda")
+    return SplatTrainStep(scene, H, W, sh_degree=3, w_pearson=0.05, w_alpha=0.01), synthetic.make_camera(3, 8, H, W, T), (N, H, W, T)
+
+
+def _forward(step, cam):
+    vm = cam.world_view_transform.t().contiguous().cuda()
+    pm = cam.projection_matrix.t().contiguous().cuda()
+    step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, step.p("table")[cam.time_index].contiguous(), None, None,
+                          forward_only=True)
+    return step.last_outputs, step.last_state
+
+
+@pytest.mark.parametrize("cfg", ["c2_kubric", "c4_iphone"])
+def test_binning_tables_are_consistent_at_full_size(cfg):
+    step, cam, (N, H, W, T) = _step(cfg)
+    (color, depth, alpha, radii), st = _forward(step, cam)
+    D = int(st.num_rendered[0])
+    assert int(st.num_rendered[1]) == 0
+    tiles_touched = st.geom["tiles_touched"].long()
+    assert int(tiles_touched.sum()) == D == int(st.extras["point_offsets"][-1])
+    assert torch.equal(st.extras["point_offsets"].long(), torch.cumsum(tiles_touched, 0))
+    assert torch.equal(radii > 0, tiles_touched > 0)
+    keys = st.extras["keys_sorted"][:D]
+    assert bool((keys[1:] >= keys[:-1]).all()), "keys not sorted"
+    vals = st.vals_sorted[:D].long()
+    assert int(vals.min()) >= 0 and int(vals.max()) < N
+    # the multiset of values = every visible Gaussian repeated tiles_touched times (checksum of checksums)
+    cnt = torch.bincount(vals, minlength=N)
+    assert torch.equal(cnt, tiles_touched)
+    # keys carry the Gaussian's own depth bits
+    dbits = st.geom["p2"][:, 1].contiguous().view(torch.int32).long() & 0xFFFFFFFF
+    assert torch.equal(keys & 0xFFFFFFFF, dbits[vals])
+    # tile ranges partition [0, D) in tile order and agree with the keys' tile ids
+    tile_of = keys >> 32
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    ranges = st.ranges.long()
+    ne = ranges[:, 1] > ranges[:, 0]
+    assert int((ranges[:, 1] - ranges[:, 0]).sum()) == D
+    assert torch.equal(torch.bincount(tile_of, minlength=gx * gy), ranges[:, 1] - ranges[:, 0])
+    starts = ranges[ne, 0]
+    assert torch.equal(tile_of[starts], torch.nonzero(ne).squeeze(1))
+    # stable order: inside a tile, equal depth bits keep ascending Gaussian index
+    same = (keys[1:] == keys[:-1])
+    assert bool((vals[1:][same] > vals[:-1][same]).all())
+    # blend identities
+    assert torch.allclose(alpha[0], 1.0 - st.final_T, atol=1e-6)
+    assert bool((st.n_contrib.long().flatten() <= (ranges[:, 1] - ranges[:, 0]).max()).all())
+    assert torch.isfinite(color).all() and torch.isfinite(depth).all()
+    assert float(alpha.min()) >= 0.0 and float(alpha.max()) <= 1.0 + 1e-6
+
+
+def test_forward_is_deterministic_and_sync_free_equals_default():
+    step, cam, _ = _step("c2_kubric")
+    (c1, d1, a1, r1), s1 = _forward(step, cam)
+    c1, d1, v1 = c1.clone(), d1.clone(), s1.vals_sorted[: int(s1.num_rendered[0])].clone()
+    engine.config.sync_free = True
+    (c2, d2, a2, r2), s2 = _forward(step, cam)
+    assert torch.equal(c1, c2) and torch.equal(d1, d2) and torch.equal(r1, r2)
+    assert torch.equal(v1, s2.vals_sorted[: int(s2.num_rendered[0])])
+
+
+def test_backward_is_linear_in_the_upstream_gradient():
+    """grads(a*g1 + g2) == a*grads(g1) + grads(g2) up to float-atomic reordering."""
+    N, H, W, T = 60_000, 256, 256, 8
+    scene = synthetic.to_device(synthetic.make_scene(N, H, W, T, seed=1), "cuda")
+    step = SplatTrainStep(scene, H, W, sh_degree=3)
+    cam = synthetic.make_camera(2, 8, H, W, T)
+    (_, _, _, _), st = _forward(step, cam)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ups = [(torch.randn(3, H, W, device="cuda", generator=g), torch.randn(1, H, W, device="cuda", generator=g),
+            torch.randn(1, H, W, device="cuda", generator=g)) for _ in range(2)]
+
+    def run(gc, gd, ga):
+        step.grads.zero_()
+        step.view_grad.zero_()
+        grads = engine.SceneGrads(st=step._setgrad("static"), dy=step._setgrad("dynamic"), means2D=step.means2D_grad,
+                                  viewmatrix=step.view_grad, motion_coeff=step.g("motion_coeff").view(step.nd, 16),
+                                  table=step.g("table"), basis_t=step.g("basis_t"))
+        engine.render_backward(st, gc, gd, ga, grads)
+        return step.grads.clone(), step.view_grad.clone()
+
+    a = 0.37
+    g1, v1 = run(*ups[0])
+    g2, v2 = run(*ups[1])
+    g3, v3 = run(*[a * x + y for x, y in zip(ups[0], ups[1])])
+    ref, refv = a * g1 + g2, a * v1 + v2
+    assert (g3 - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+    assert (v3 - refv).abs().max().item() <= 2e-4 * refv.abs().max().item()
+    # zero upstream gradient -> exactly zero parameter gradients
+    z, zv = run(torch.zeros_like(ups[0][0]), torch.zeros_like(ups[0][1]), torch.zeros_like(ups[0][2]))
+    assert z.abs().max().item() == 0.0 and zv.abs().max().item() == 0.0
+
+
+def test_training_step_reduces_the_loss():
+    """A few fused-Adam steps on the flat buffers lower the photometric loss (end-to-end sanity)."""
+    from rodygs_b200 import _lib
+    N, H, W, T = 40_000, 192, 256, 6
+    scene = synthetic.to_device(synthetic.make_scene(N, H, W, T, seed=2), "cuda")
+    step = SplatTrainStep(scene, H, W, sh_degree=3, w_pearson=0.0)
+    cam = synthetic.make_camera(1, 8, H, W, T)
+    vm = cam.world_view_transform.t().contiguous().cuda()
+    pm = cam.projection_matrix.t().contiguous().cuda()
+    bt = step.p("table")[cam.time_index].clone()
+    gt = torch.rand(3, H, W, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)) * 0.5 + 0.25
+    lib = _lib.load()
+    m, v = torch.zeros_like(step.params), torch.zeros_like(step.params)
+    losses = []
+    for it in range(1, 13):
+        lp = step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, bt, gt, None)
+        losses.append(float(lp[0]))
+        _lib.check(lib.rdg_adam(step.params.data_ptr(), step.grads.data_ptr(), m.data_ptr(), v.data_ptr(), step.params.numel(),
+                                5e-3, 0.9, 0.999, 1e-15, it, 1.0, _lib.stream_ptr()))
+    assert losses[-1] < 0.9 * losses[0], losses
+
+
+def test_fused_adam_matches_torch_adam():
+    """rdg_adam == torch.optim.Adam(eps=1e-15) (rodygs_static.py:106-149) on a flat buffer."""
+    from rodygs_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    p0 = torch.randn(100_003, device="cuda", generator=g)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1.6e-4, eps=1e-15)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    for it in range(1, 5):
+        grad = torch.randn(p0.shape, device="cuda", generator=g)
+        p_ref.grad = grad.clone()
+        opt.step()
+        _lib.check(lib.rdg_adam(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 1.6e-4, 0.9, 0.999,
+                                1e-15, it, 1.0, _lib.stream_ptr()))
+    assert torch.allclose(p, p_ref.detach(), rtol=1e-5, atol=1e-7)
