@@ -106,6 +106,8 @@ typedef struct RdgGeom {
     float* p2;               /* [N,2] b, view-space depth */
     uint8_t* clamped;        /* [N]   bit c set = channel c clamped at 0 */
     float* dbg_activated;    /* optional [N,11] (xyz, scale, quat, opacity) as used by the kernel; NULL to skip */
+    uint32_t* tile_count;    /* optional [tiles+1]: preprocess counts the Gaussians touching each tile (zeroed inside);
+                              * required by rdg_bin_tiles */
 } RdgGeom;
 
 /* Tile-binning result. */
@@ -156,6 +158,16 @@ int rdg_preprocess_fwd(const RdgScene* scene, const RdgView* view, const RdgGeom
 
 /* bytes of scratch rdg_bin needs for N Gaussians and at most d_cap duplicates. */
 int64_t rdg_bin_workspace_bytes(int64_t n, int64_t d_cap, int32_t height, int32_t width);
+
+/* Same result (sorted values, sorted keys, ranges, duplicate count) as rdg_bin, computed the B200 way:
+ * per-tile counts come from preprocess (geom->tile_count), a tiny scan turns them into tile segments
+ * (= the ranges), instances are dropped into their tile's segment with one returning atomic each and
+ * every tile is then sorted by (depth bits, Gaussian id) inside ONE CTA in shared memory - two passes
+ * over the duplicates in HBM instead of ten.  bins->point_offsets / keys_unsorted / vals_unsorted are not
+ * produced (they only exist in the emission order of rdg_bin); bins->keys_sorted may be NULL. */
+int64_t rdg_bin_tiles_workspace_bytes(int64_t n, int64_t d_cap, int32_t height, int32_t width);
+int rdg_bin_tiles(int64_t n, const RdgGeom* geom, int32_t height, int32_t width, int64_t d_cap,
+                  const RdgBins* bins, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* scan + duplicateWithKeys + radix sort + identifyTileRanges (§8 a8). */
 int rdg_bin(int64_t n, const RdgGeom* geom, int32_t height, int32_t width, int64_t d_cap,

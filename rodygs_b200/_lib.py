@@ -38,7 +38,7 @@ class RdgView(C.Structure):
 
 class RdgGeom(C.Structure):
     _fields_ = [("radii", c_ptr), ("tiles_touched", c_ptr), ("p0", c_ptr), ("p1", c_ptr), ("p2", c_ptr),
-                ("clamped", c_ptr), ("dbg_activated", c_ptr)]
+                ("clamped", c_ptr), ("dbg_activated", c_ptr), ("tile_count", c_ptr)]
 
 
 class RdgBins(C.Structure):
@@ -70,6 +70,9 @@ SYMBOLS = {
     "rdg_bin_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "rdg_bin": (C.c_int, [C.c_int64, C.POINTER(RdgGeom), C.c_int32, C.c_int32, C.c_int64, C.POINTER(RdgBins),
                           c_ptr, C.c_int64, c_ptr]),
+    "rdg_bin_tiles_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
+    "rdg_bin_tiles": (C.c_int, [C.c_int64, C.POINTER(RdgGeom), C.c_int32, C.c_int32, C.c_int64, C.POINTER(RdgBins),
+                                c_ptr, C.c_int64, c_ptr]),
     "rdg_blend_fwd": (C.c_int, [C.c_int64, C.POINTER(RdgGeom), C.POINTER(RdgBins), C.POINTER(RdgView),
                                 C.POINTER(RdgImage), c_ptr]),
     "rdg_blend_bwd": (C.c_int, [C.c_int64, C.POINTER(RdgGeom), C.POINTER(RdgBins), C.POINTER(RdgView),

@@ -28,6 +28,7 @@ SOURCES = {
     "api.cu": [],
     "preprocess_fwd.cu": ["-fmad=false"],
     "binning.cu": ["-fmad=false"],
+    "binning_tiles.cu": ["-fmad=false"],
     "blend.cu": [],
     "preprocess_bwd.cu": [],
     "loss.cu": [],

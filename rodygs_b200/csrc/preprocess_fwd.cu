@@ -115,7 +115,13 @@ __global__ void __launch_bounds__(RDG_BLOCK) preprocess_fwd_kernel(const PreFwdP
                 const int rmaxx = min(cam.gx, max(0, (int)((px + rad_f + 15.0f) / 16.0f)));
                 const int rmaxy = min(cam.gy, max(0, (int)((py + rad_f + 15.0f) / 16.0f)));
                 const int cntt = (rmaxx - rminx) * (rmaxy - rminy);
-                if (cntt > 0) { radius = (int)rad_f; tiles = (unsigned)cntt; vis = true; tz = pr.tz; }
+                if (cntt > 0) {
+                    radius = (int)rad_f; tiles = (unsigned)cntt; vis = true; tz = pr.tz;
+                    if (p.geom.tile_count) {   // per-tile population for the tile-bucketed binning
+                        for (int yy = rminy; yy < rmaxy; ++yy)
+                            for (int xx = rminx; xx < rmaxx; ++xx) atomicAdd(&p.geom.tile_count[yy * cam.gx + xx], 1u);
+                    }
+                }
             }
         }
         if (use_sh) {
@@ -218,6 +224,10 @@ extern "C" int rdg_preprocess_fwd(const RdgScene* scene, const RdgView* view, co
     // persistent grid: a multiple of the SM count (4 CTAs of 46 KB fit per SM)
     const int grid = (int)(chunks < (int64_t)RDG_SM_COUNT * 4 ? chunks : (int64_t)RDG_SM_COUNT * 4);
     cudaStream_t s = (cudaStream_t)stream;
+    if (geom->tile_count) {
+        const int tiles = ((view->width + RDG_TILE - 1) / RDG_TILE) * ((view->height + RDG_TILE - 1) / RDG_TILE);
+        RDG_CUDA(cudaMemsetAsync(geom->tile_count, 0, (size_t)(tiles + 1) * sizeof(uint32_t), s));
+    }
     const int rc = scene->raw ? launch_fwd_deg<true>(p, view->sh_degree, grid, smem, s)
                               : launch_fwd_deg<false>(p, view->sh_degree, grid, smem, s);
     if (rc) return rc;

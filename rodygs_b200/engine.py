@@ -39,6 +39,11 @@ class Config:
     min_capacity: int = 1 << 16
     debug_keep_unsorted: bool = False   # tests: keep duplicateWithKeys' output
     debug_activated: bool = False       # tests: dump the activated parameters the kernel used
+    # "tiles": tile-bucketed binning (per-tile shared-memory sort, rdg_bin_tiles) - the fast path.
+    # "lsd":   scan + duplicateWithKeys + global LSD radix sort (rdg_bin); also produces the
+    #          emission-order arrays (point_offsets, unsorted keys/values) that the tests pin.
+    binning: str = "tiles"
+    emit_sorted_keys: bool = True       # write the sorted 64-bit keys (only verification reads them)
 
 
 config = Config()
@@ -204,6 +209,7 @@ def _geom_struct(g: dict) -> RdgGeom:
     out.p0, out.p1, out.p2 = ptr(g["p0"]), ptr(g["p1"]), ptr(g["p2"])
     out.clamped = ptr(g["clamped"])
     out.dbg_activated = ptr(g.get("dbg_activated"))
+    out.tile_count = ptr(g.get("tile_count"))
     return out
 
 
@@ -250,6 +256,9 @@ def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = T
     }
     if config.debug_activated:
         geom["dbg_activated"] = torch.zeros(n, 11, **f32)
+    use_tiles = config.binning == "tiles" and not config.debug_keep_unsorted
+    if use_tiles:
+        geom["tile_count"] = torch.empty(tiles_of(H, W) + 1, dtype=torch.int32, device=dev)
     sc_s, vw_s, gm_s = _scene_struct(scene), _view_struct(view), _geom_struct(geom)
     check(lib.rdg_preprocess_fwd(C.byref(sc_s), C.byref(vw_s), C.byref(gm_s), stream))
     if stage_hook:
@@ -264,9 +273,10 @@ def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = T
     extras = {}
     while True:
         d_cap = int(st["cap"])
-        keys = torch.empty(d_cap, dtype=torch.int64, device=dev)
+        want_keys = config.emit_sorted_keys or not use_tiles
+        keys = torch.empty(d_cap, dtype=torch.int64, device=dev) if want_keys else None
         vals = torch.empty(d_cap, dtype=torch.int32, device=dev)
-        ws_bytes = int(lib.rdg_bin_workspace_bytes(n, d_cap, H, W))
+        ws_bytes = int((lib.rdg_bin_tiles_workspace_bytes if use_tiles else lib.rdg_bin_workspace_bytes)(n, d_cap, H, W))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         bins = RdgBins()
         bins.keys_sorted, bins.vals_sorted = ptr(keys), ptr(vals)
@@ -275,7 +285,8 @@ def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = T
             extras["keys_unsorted"] = torch.empty(d_cap, dtype=torch.int64, device=dev)
             extras["vals_unsorted"] = torch.empty(d_cap, dtype=torch.int32, device=dev)
             bins.keys_unsorted, bins.vals_unsorted = ptr(extras["keys_unsorted"]), ptr(extras["vals_unsorted"])
-        check(lib.rdg_bin(n, C.byref(gm_s), H, W, d_cap, C.byref(bins), ptr(ws), ws_bytes, stream))
+        check((lib.rdg_bin_tiles if use_tiles else lib.rdg_bin)(n, C.byref(gm_s), H, W, d_cap, C.byref(bins), ptr(ws),
+                                                                ws_bytes, stream))
         if config.sync_free:
             host = torch.empty(2, dtype=torch.int32, pin_memory=True)
             host.copy_(num_rendered, non_blocking=True)

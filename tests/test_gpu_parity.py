@@ -79,16 +79,20 @@ def _debug_off():
     engine.config.debug_keep_unsorted = False
     engine.config.debug_activated = False
     engine.config.sync_free = False
+    engine.config.binning = "tiles"
 
 
+@pytest.mark.parametrize("binning", ["tiles", "lsd"])
 @pytest.mark.parametrize("H,W,n,deg", [(96, 128, 3000, 3), (100, 75, 2000, 1), (64, 64, 1500, 0), (160, 256, 12000, 2)])
-def test_boundary_forward_bitexact_and_images(H, W, n, deg):
-    """radii / keys / order / ranges bit-exact, images within 1e-4 (ragged sizes included)."""
+def test_boundary_forward_bitexact_and_images(H, W, n, deg, binning):
+    """radii / keys / order / ranges bit-exact, images within 1e-4 (ragged sizes included), for both
+    binning implementations: "tiles" (per-tile shared-memory sort) and "lsd" (scan + duplicateWithKeys +
+    global radix sort, which also exposes the emission-order arrays)."""
     sc, cam = helpers.small_scene(n, H, W, 6, seed=n)
     acts = helpers.activated_concat(sc, cam)
     bg = torch.tensor([0.1, 0.3, 0.2])
     orc = _run_oracle(acts, cam, bg, deg)["out"]
-    engine.config.debug_keep_unsorted = True
+    engine.config.debug_keep_unsorted = binning == "lsd"
     xyz, op, scl, rot, feat = [t.cuda() for t in acts]
     scene = engine.SceneArgs(st=engine.SetArgs(xyz=xyz, scaling=scl, rotation=rot, opacity=op, sh_dc=feat, sh_rest=feat,
                                                sh_dc_stride=48, sh_rest_stride=48, sh_rest_offset=3), raw=False)
@@ -101,9 +105,10 @@ def test_boundary_forward_bitexact_and_images(H, W, n, deg):
     assert torch.equal(radii.cpu(), orc.radii), "radii differ"
     assert torch.equal(state.geom["tiles_touched"].cpu(), orc.pp.tiles_touched), "tiles_touched differ"
     assert D == orc.bn.keys.numel(), "duplicate count differs"
-    assert torch.equal(state.extras["point_offsets"].cpu().long(), orc.bn.point_offsets), "scan differs"
-    assert torch.equal(state.extras["keys_unsorted"][:D].cpu(), orc.bn.keys_unsorted), "duplicateWithKeys keys differ"
-    assert torch.equal(state.extras["vals_unsorted"][:D].cpu(), orc.bn.vals_unsorted), "duplicateWithKeys values differ"
+    if binning == "lsd":
+        assert torch.equal(state.extras["point_offsets"].cpu().long(), orc.bn.point_offsets), "scan differs"
+        assert torch.equal(state.extras["keys_unsorted"][:D].cpu(), orc.bn.keys_unsorted), "duplicateWithKeys keys differ"
+        assert torch.equal(state.extras["vals_unsorted"][:D].cpu(), orc.bn.vals_unsorted), "duplicateWithKeys values differ"
     assert torch.equal(state.extras["keys_sorted"][:D].cpu(), orc.bn.keys), "sorted keys differ"
     assert torch.equal(state.vals_sorted[:D].cpu(), orc.bn.vals), "sorted order differs"
     assert torch.equal(state.ranges.cpu(), orc.bn.ranges), "tile ranges differ"
@@ -269,7 +274,6 @@ def test_fused_path_bitexact_given_its_own_activations():
     H, W, n, T = 64, 96, 2000, 5
     sc, cam = helpers.small_scene(n, H, W, T, seed=33)
     engine.config.debug_activated = True
-    engine.config.debug_keep_unsorted = True
     dev = "cuda"
     def mk(d):
         return engine.SetArgs(xyz=d["xyz"].to(dev), scaling=d["scaling"].to(dev), rotation=d["rotation"].to(dev),
