@@ -246,9 +246,8 @@ __global__ void __launch_bounds__(RDG_BLOCK) radix_scatter_kernel(const uint64_t
         const uint32_t i = wbase + r * 32 + lane;
         const bool valid = i < n;
         key[r] = valid ? keys_in[i] : 0;
-        // invalid lanes get a digit outside the bin range so they never match a valid one
-        const uint32_t d = valid ? ((uint32_t)(key[r] >> shift) & mask) : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
+        const uint32_t peers = rdg_match_digit(d, bits, __ballot_sync(0xffffffffu, valid));
         const int leader = __ffs(peers) - 1;
         const uint32_t below = __popc(peers & ((1u << lane) - 1u));
         uint32_t old = 0;

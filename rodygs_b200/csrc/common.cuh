@@ -96,6 +96,19 @@ __device__ __forceinline__ void rdg_load_cam(RdgCam& c, const float* __restrict_
     c.gy = (height + RDG_TILE - 1) / RDG_TILE;
 }
 
+// Lanes of `valid` that hold the same `bits`-bit digit as the caller.  One VOTE per digit bit:
+// on sm_100 this is several times faster than match.any.sync (MATCH serialises over the distinct
+// values, and radix digits are almost all distinct inside a warp) - ncu r01, tile_sort_kernel.
+__device__ __forceinline__ unsigned rdg_match_digit(uint32_t d, int bits, unsigned valid) {
+    unsigned peers = valid;
+    for (int b = 0; b < bits; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
 // dL/dtable[t][k][j] = -sum_{i : birth frame t} c_i[k] g_i[j];  dL/dB(t)[k][j] = +sum_i c_i[k] g_i[j].
 // grid (T, DT_SLICES); thread e < K*7 owns one (k, j) and accumulates in a register over the
 // frame's Gaussians, staged 64 at a time in shared memory - no atomics until the final add.
-#define DT_SLICES 8
+#define DT_SLICES 32
 #define DT_TILE 64
 __global__ void __launch_bounds__(128) dtable_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ offsets,
                                                      const float* __restrict__ coeff, const float* __restrict__ g7, int num_basis,
