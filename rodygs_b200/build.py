@@ -30,6 +30,7 @@ SOURCES = {
     "binning.cu": ["-fmad=false"],
     "binning_tiles.cu": ["-fmad=false"],
     "blend.cu": [],
+    "blend_v1.cu": [],
     "preprocess_bwd.cu": [],
     "loss.cu": [],
 }

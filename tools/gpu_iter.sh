@@ -1,0 +1,40 @@
+#!/bin/bash
+# One development iteration on the GPU box: parity tests, bench (optionally A/B against an env switch),
+# and an ncu capture of chosen kernels exported to CSV on the box (the .ncu-rep is dropped when large).
+#   NCU_K   regex of kernels to capture with --set full (empty: skip)      NCU_S / NCU_C   skip / count
+#   AB_ENV  e.g. "RDG_BLEND_V1=1": also run the bench with that variable set
+#   TESTS   pytest -k expression (default: all gpu tests)
+mkdir -p gpurun_out
+rm -f gpurun_out/*.ncu-rep
+timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x ${TESTS:+-k "$TESTS"} > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -15 gpurun_out/pytest_gpu.log
+summ() {
+python - "$1" <<'PY'
+import json, sys
+for l in open(sys.argv[1]):
+    if l.startswith('{'):
+        d=json.loads(l); print(sys.argv[1], 'ms/step',round(d['ms_per_step'],3),'it/s',round(d['value'],1),'e2e',round(d['e2e']['value'],1)); print({k:round(v,3) for k,v in d.get('stage_ms',{}).items()}); print(d['roofline']['kernel'], round(d['roofline']['frac'],4), 'step frac', round(d['step_roofline']['frac'],4), d['clocks'])
+    elif 'rror' in l or 'exit' in l: print(l.strip()[:300])
+PY
+}
+timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_c4.log 2>&1; echo "exit $?" >> gpurun_out/bench_c4.log
+summ gpurun_out/bench_c4.log
+if [ -n "$AB_ENV" ]; then
+  env $AB_ENV timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_c4_ab.log 2>&1; echo "exit $?" >> gpurun_out/bench_c4_ab.log
+  summ gpurun_out/bench_c4_ab.log
+fi
+if [ -n "$EXTRA_BENCH" ]; then
+  timeout 900 python bench.py $EXTRA_BENCH --no-cpu-baseline > gpurun_out/bench_extra.log 2>&1; echo "exit $?" >> gpurun_out/bench_extra.log
+  summ gpurun_out/bench_extra.log
+fi
+if [ -n "$NCU_K" ]; then
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$NCU_K" -s ${NCU_S:-12} -c ${NCU_C:-2} -o gpurun_out/prof_k -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_k.log 2>&1
+  echo "ncu exit $?"
+  ncu -i gpurun_out/prof_k.ncu-rep --page raw --csv > gpurun_out/prof_k_raw.csv 2>/dev/null
+  ncu -i gpurun_out/prof_k.ncu-rep --page source --csv --print-source sass > gpurun_out/prof_k_sass.csv 2>/dev/null
+  ncu -i gpurun_out/prof_k.ncu-rep --page details > gpurun_out/prof_k_details.txt 2>/dev/null
+  sz=$(stat -c %s gpurun_out/prof_k.ncu-rep); if [ "$sz" -gt 25000000 ]; then rm -f gpurun_out/prof_k.ncu-rep; echo "rep dropped ($sz bytes)"; fi
+fi
+ls -la gpurun_out/ | head -30
+du -sh gpurun_out
