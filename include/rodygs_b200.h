@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RDG_ABI_VERSION 2
+#define RDG_ABI_VERSION 3
 #define RDG_TILE 16
 #define RDG_NUM_BASIS_MAX 16
 
@@ -195,11 +195,31 @@ int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, const RdgGeom
 int64_t rdg_l1_dssim_workspace_bytes(int32_t channels, int32_t height, int32_t width);
 
 /* loss = w_l1 * mean|x-y| + w_dssim * (1 - mean SSIM(x,y))   (loss_utils.py:19-20,57-97;
- * losses.py:61-107).  out_loss (device, 3 floats) = {loss, l1, ssim}; it must be zeroed
- * by the caller.  dL_dpred [C,H,W] receives d loss / d pred (may be NULL: forward only). */
+ * losses.py:61-107).  out_loss (device, 3 floats) = {loss, l1, ssim}.  dL_dpred [C,H,W] receives d loss / d pred (may be NULL: forward only). */
 int rdg_l1_dssim(const float* pred, const float* gt, int32_t channels, int32_t height, int32_t width,
                  float w_l1, float w_dssim, float* out_loss, float* dL_dpred,
                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Optional terms that ride on the photometric pass of rdg_losses (NULL pointers / zero weights = off):
+ * the global Pearson depth regulariser (losses.py:110-129, loss_utils.py:100-117) and the benchmark's
+ * alpha regulariser w * mean(1 - alpha). */
+typedef struct RdgLossTerms {
+    const float* depth;      /* [1,H,W] rendered depth */
+    const float* gt_depth;   /* [1,H,W] */
+    float w_pearson;         /* weight applied to the gradient written to dL_ddepth */
+    float pearson_eps;       /* 1e-6 in the reference */
+    float* dL_ddepth;        /* [1,H,W] overwritten with w_pearson * d(1 - Pearson)/d depth; may be NULL */
+    const float* alpha;      /* [1,H,W] rendered alpha */
+    float w_alpha;
+    float* dL_dalpha;        /* [1,H,W] overwritten with -w_alpha / (H W); may be NULL */
+} RdgLossTerms;
+
+/* The whole per-iteration loss stage in three launches: rdg_l1_dssim plus the optional terms above.
+ * out_loss (device, 8 floats) = {photometric loss, l1, ssim, 1 - Pearson, w_alpha * mean(1 - alpha), -, -, -};
+ * entries of disabled terms are left untouched.  Workspace as for rdg_l1_dssim. */
+int rdg_losses(const float* pred, const float* gt, int32_t channels, int32_t height, int32_t width,
+               float w_l1, float w_dssim, const RdgLossTerms* extra, float* out_loss, float* dL_dpred,
+               void* workspace, int64_t workspace_bytes, void* stream);
 
 /* 1 - Pearson(pred, gt) with the unbiased std (loss_utils.py:100-117), over n_boxes boxes
  * given as (row0, col0, rows, cols) int32 quadruples on the device; box 0 = the whole image

@@ -60,6 +60,11 @@ class RdgSceneGrad(C.Structure):
                 ("viewmatrix", c_ptr), ("motion_coeff", c_ptr), ("table", c_ptr), ("basis_t", c_ptr), ("g7_scratch", c_ptr)]
 
 
+class RdgLossTerms(C.Structure):
+    _fields_ = [("depth", c_ptr), ("gt_depth", c_ptr), ("w_pearson", C.c_float), ("pearson_eps", C.c_float),
+                ("dL_ddepth", c_ptr), ("alpha", c_ptr), ("w_alpha", C.c_float), ("dL_dalpha", c_ptr)]
+
+
 # every symbol include/rodygs_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "rdg_abi_version": (C.c_int, []),
@@ -82,6 +87,8 @@ SYMBOLS = {
     "rdg_l1_dssim_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "rdg_l1_dssim": (C.c_int, [c_ptr, c_ptr, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, c_ptr, c_ptr,
                                c_ptr, C.c_int64, c_ptr]),
+    "rdg_losses": (C.c_int, [c_ptr, c_ptr, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.POINTER(RdgLossTerms),
+                             c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr]),
     "rdg_pearson": (C.c_int, [c_ptr, c_ptr, C.c_int32, C.c_int32, c_ptr, c_ptr, C.c_int32, C.c_float, c_ptr, c_ptr,
                               c_ptr, c_ptr]),
     "rdg_adam": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
@@ -105,7 +112,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.rdg_abi_version() != 2:
+    if lib.rdg_abi_version() != 3:
         raise RuntimeError("librodygs_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -2,18 +2,23 @@
 // depth-sorted per-tile lists.  SURVEY.md §8 rows a9 / a10; spec: SURVEY.md
 // App. A.4-A.6 == oracle/splat_oracle.py::blend (+ autograd).
 //
-// B200 mapping (v2, profiles/README.md has the measured history)
+// B200 mapping (v3, profiles/README.md has the measured history)
 //  * one CTA of 4 warps per 16x16 tile.  The tile is cut into sixteen 4x4-pixel sub-tiles; a
 //    quarter-warp (8 lanes) owns one sub-tile and every lane owns TWO vertically adjacent
 //    pixels, so the Gaussian record a lane fetches from shared memory (the crossbar is the
 //    co-limiter of this loop, ncu r01) and the x-dependent half of the conic are used twice.
 //  * per-tile batches of 128 list entries are staged in shared memory as three packed
-//    records (16 + 16 + 8 bytes).  The staging thread solves the alpha >= 1/255 ellipse of its
-//    Gaussian row by row and turns it into a 16-bit mask of the sub-tiles it can reach
-//    (conservative margins; the exact rule stays per pixel).  Each warp compacts the batch
-//    into one list per quarter with ballot/popc; the four quarters then walk their own lists
-//    in lock step (3.0 (sub-tile, Gaussian) visits per list entry at the bench config,
-//    0.84 warp iterations per entry against 2.3 for the 8x4-per-warp bounding-box version).
+//    records (16 + 16 + 8 bytes) by cp.async (LDGSTS) into a double buffer: batch k+1 is in
+//    flight while batch k is blended, one barrier per batch in the forward pass.
+//  * the staging thread solves the alpha >= 1/255 ellipse of its Gaussian against the four
+//    4-row bands of the tile and turns it into a 16-bit mask of the sub-tiles it can reach
+//    (conservative margins; the exact rule stays per pixel).  The forward pass stores the mask
+//    per list entry (2 B) and the backward pass reads it back.  Each warp compacts the batch
+//    into one list per quarter with ballot/popc and pads the four lists to a common length
+//    with a null entry (opacity 0), so the inner loop has no per-quarter validity test; the
+//    four quarters walk their own lists in lock step (3.0 (sub-tile, Gaussian) visits per list
+//    entry at the bench config, 0.84 warp iterations per entry against 2.3 for the
+//    8x4-per-warp bounding-box version).
 //  * backward: a lane first adds the ten partial gradients of its two pixels, the quarter
 //    reduce-scatters them in 10 shuffles (5+3+2) and every lane stores the total it owns into
 //    a per-(sub-tile, Gaussian) record in shared memory - a plain store, no atomics in the
@@ -29,28 +34,58 @@
 #define SUBS 16                 // 4x4-pixel sub-tiles per tile
 #define BATCH 128               // list entries staged per round == threads per CTA
 #define NWARP (BATCH / 32)
-#define LROW (BATCH + 2)        // list row stride (u16): rows of neighbouring sub-tiles start in different banks
+#define NSLOT (BATCH + 1)       // + the null slot (opacity 0) that pads the lists
+#define LROW (BATCH + 1)        // list row stride (u32): rows of neighbouring sub-tiles start in different banks
 #define POOL 512                // (sub-tile, entry) gradient records per round (backward)
-#define PREC 12                 // floats per record (10 used; 48-byte rows for vector loads)
+#define PREC 10                 // floats per record
+#define NULL_ENTRY ((uint32_t)BATCH | ((uint32_t)(POOL * PREC * 4) << 8))   // null slot, scratch record
 #define FULL 0xffffffffu
 
 extern "C" int rdg_blend_fwd_v1(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view, const RdgImage* out, void* stream);
 extern "C" int rdg_blend_bwd_v1(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view, const RdgImage* fwd,
-                     const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, float* acc, void* stream);
+                                const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, float* acc, void* stream);
 
 struct __align__(16) Staged {
-    float4 a[BATCH];              // px, py, A, B
-    float4 b[BATCH];              // C, opacity, r, g
-    float2 c[BATCH];              // b, depth
-    uint32_t id[BATCH];
-    uint16_t mask[BATCH];         // bit s: may touch sub-tile s (s = 4 * sub_y + sub_x)
+    float4 a[2][NSLOT];           // px, py, A, B          (double buffered: batch k+1 lands while batch k is blended)
+    float4 b[2][NSLOT];           // C, opacity, r, g
+    float2 c[2][NSLOT];           // b, depth
+    uint32_t id[2][BATCH];
+    uint16_t mask[2][BATCH];      // bit s: may touch sub-tile s (s = 4 * sub_y + sub_x)
     uint16_t ebase[BATCH];        // backward: first gradient record of this entry
-    uint16_t list[SUBS][LROW];    // per sub-tile compacted entries: slot | (record << 7)
+    uint32_t list[SUBS][LROW];    // per sub-tile compacted entries: slot | (record byte offset << 8)
 };
 
 __device__ __forceinline__ float rdg_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rdg_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rdg_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// shared-window accesses by 32-bit address: the inner loops index three arrays with one offset
+// and keep the window bases in registers
+__device__ __forceinline__ uint32_t rdg_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t rdg_lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 rdg_lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 rdg_lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rdg_sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void rdg_cp16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void rdg_cp8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void rdg_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void rdg_cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // alpha = min(0.99, o * exp(power)), power = -(A dx^2 + C dy^2)/2 - B dx dy.  Identical
 // instruction sequence in both passes so that the skip decisions replayed by the backward
@@ -64,31 +99,48 @@ __device__ __forceinline__ bool rdg_alpha(float Adx2, float Bdx, float C, float 
     return (power <= 0.0f) && (alpha >= RDG_ALPHA_MIN);
 }
 
-// 16-bit mask of the 4x4 sub-tiles that the alpha >= 1/255 ellipse of this Gaussian reaches:
-// with u = x - px, v = y - py the rule is  A u^2 + 2 B u v + C v^2 <= tau = 2 ln(255 o);
-// for pixel row v that is  u in [(-B v - sqrt(tau A - v^2 det)) / A, (-B v + sqrt(..)) / A].
-// Conservative (0.5 % on tau, 0.02 px on every bound); the exact rule stays per pixel.
+// 16-bit mask of the 4x4 sub-tiles that the alpha >= 1/255 ellipse of this Gaussian reaches.
+// With u = x - px, v = y - py the rule is  A u^2 + 2 B u v + C v^2 <= tau = 2 ln(255 o).  At height v
+// the ellipse spans u-(v) .. u+(v) = (-B v -+ sqrt(tau A - v^2 det)) / A; u+ is concave and peaks at
+// v* = -B ex / C with u+ = ex = sqrt(tau C / det), u- mirrors it.  So over the rows of one band the
+// span is bounded by the values at the band's two edges (clamped to the ellipse's own height) and by
+// +-ex when v* (-v*) falls inside the band: five edge evaluations for the four bands, no loop over
+// rows.  Conservative (0.5 % on tau, half a pixel row on each band, 0.03 px on every bound); the exact
+// rule stays per pixel.
 __device__ __forceinline__ unsigned rdg_sub_mask(const float4 a, const float4 b, float tile_x0, float tile_y0) {
     const float A = a.z, B = a.w, C = b.x, o = b.y;
     if (!(o >= RDG_ALPHA_MIN)) return 0u;        // o * exp(power <= 0) can never reach 1/255
     const float tau = 2.0f * __logf(255.0f * o) * 1.005f + 2e-3f;
     const float det = A * C - B * B;
     if (!(det > 0.0f) || !(A > 0.0f)) return 0xffffu;
-    const float tA = tau * A;
-    const float ey = rdg_sqrt(__fdividef(tA, det)) * 1.001f + 0.02f;
+    const float tA = tau * A, inv_det = rdg_rcp(det);
+    const float ey = rdg_sqrt(tA * inv_det) * 1.001f, ex = rdg_sqrt(tau * C * inv_det) * 1.001f;
     const float cx = a.x - tile_x0, cy = a.y - tile_y0;
-    if (!(ey < 1e6f) || !(fabsf(cx) < 1e6f) || !(fabsf(cy) < 1e6f)) return 0xffffu;
-    const int r0 = max(0, (int)ceilf(cy - ey)), r1 = min(RDG_TILE - 1, (int)floorf(cy + ey));
+    if (!(ey < 1e6f) || !(ex < 1e6f) || !(fabsf(cx) < 1e6f) || !(fabsf(cy) < 1e6f)) return 0xffffu;
     const float invA = rdg_rcp(A);
+    const float vstar = -B * ex * rdg_rcp(C);
+    const float mg = 0.03f + 1e-3f * ex;
+    float up[5], um[5], vk[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        vk[k] = (float)(4 * k) - 0.5f - cy;
+        const float vc = fminf(fmaxf(vk[k], -ey), ey);
+        const float h = rdg_sqrt(fmaxf(tA - vc * vc * det, 0.0f)) * invA;
+        const float mid = -B * vc * invA;
+        up[k] = mid + h;
+        um[k] = mid - h;
+    }
     unsigned m = 0;
-    for (int r = r0; r <= r1; ++r) {
-        const float v = (float)r - cy;
-        const float D = fmaxf(tA - v * v * det, 0.0f);
-        const float h = rdg_sqrt(D) * invA * 1.001f + 0.02f;
-        const float mid = cx - B * v * invA;
-        const float lo = fmaxf(mid - h, -1.0f), hi = fminf(mid + h, (float)RDG_TILE);   // NaN -> whole row
-        const int c0 = max(0, (int)ceilf(lo)), c1 = min(RDG_TILE - 1, (int)floorf(hi));
-        if (c0 <= c1) m |= (((2u << (c1 >> 2)) - 1u) & ~((1u << (c0 >> 2)) - 1u)) << (4 * (r >> 2));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const bool rows = (vk[k] <= ey + 0.03f) && (vk[k + 1] >= -ey - 0.03f);
+        const bool peak_r = (vstar >= vk[k] - 0.03f) && (vstar <= vk[k + 1] + 0.03f);
+        const bool peak_l = (-vstar >= vk[k] - 0.03f) && (-vstar <= vk[k + 1] + 0.03f);
+        const float hi = peak_r ? ex : fmaxf(up[k], up[k + 1]);
+        const float lo = peak_l ? -ex : fminf(um[k], um[k + 1]);
+        const float xl = fmaxf(cx + lo - mg, -1.0f), xh = fminf(cx + hi + mg, (float)RDG_TILE);
+        const int c0 = max(0, (int)ceilf(xl)), c1 = min(RDG_TILE - 1, (int)floorf(xh));
+        if (rows && c0 <= c1) m |= (((2u << (c1 >> 2)) - 1u) & ~((1u << (c0 >> 2)) - 1u)) << (4 * k);
     }
     return m;
 }
@@ -96,15 +148,16 @@ __device__ __forceinline__ unsigned rdg_sub_mask(const float4 a, const float4 b,
 // sub-tile of quarter q of warp w: the warp owns a 2x2 block of sub-tiles (an 8x8 pixel region)
 __device__ __forceinline__ int rdg_sub_of(int warp, int q) { return (2 * (warp >> 1) + (q >> 1)) * 4 + 2 * (warp & 1) + (q & 1); }
 
-// Build the lists of this warp's four quarters from mask[0..cnt) (order preserved).
-// live: bit q set = quarter q still has work.  WITH_E: append the gradient record index.
+// Build the lists of this warp's four quarters from mask[0..cnt) (order preserved) and pad them to a
+// common length with the null entry.  live: bit q set = quarter q still has work.  WITH_E: append the
+// byte offset of the entry's gradient record.  Returns the common length.
 template <bool WITH_E>
-__device__ __forceinline__ void rdg_compact4(Staged& sm, int cnt, int warp, int lane, unsigned live, int (&n)[4]) {
-    n[0] = n[1] = n[2] = n[3] = 0;
+__device__ __forceinline__ int rdg_compact4(Staged& sm, const uint16_t* mask, int cnt, int warp, int lane, unsigned live) {
+    int n[4] = {0, 0, 0, 0};
     const unsigned lt = (1u << lane) - 1u;
     for (int g = 0; g * 32 < cnt; ++g) {
         const int j = g * 32 + lane;
-        const unsigned m = (j < cnt) ? (unsigned)sm.mask[j] : 0u;
+        const unsigned m = (j < cnt) ? (unsigned)mask[j] : 0u;
         const unsigned eb = WITH_E ? (unsigned)sm.ebase[j] : 0u;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -113,13 +166,28 @@ __device__ __forceinline__ void rdg_compact4(Staged& sm, int cnt, int warp, int 
             const unsigned bal = __ballot_sync(FULL, bit);
             if (bit) {
                 unsigned e = (unsigned)j;
-                if (WITH_E) e |= (eb + __popc(m & ((1u << s) - 1u))) << 7;
-                sm.list[s][n[q] + __popc(bal & lt)] = (uint16_t)e;
+                if (WITH_E) e |= ((eb + __popc(m & ((1u << s) - 1u))) * (PREC * 4)) << 8;
+                sm.list[s][n[q] + __popc(bal & lt)] = e;
             }
             n[q] += __popc(bal);
         }
     }
+    const int nmax = max(max(n[0], n[1]), max(n[2], n[3]));
+    const int q = lane >> 3;
+    const int my_n = q == 0 ? n[0] : (q == 1 ? n[1] : (q == 2 ? n[2] : n[3]));
+    uint32_t* row = sm.list[rdg_sub_of(warp, q)];
+    for (int k = my_n + (lane & 7); k < nmax; k += 8) row[k] = NULL_ENTRY;
     __syncwarp();
+    return nmax;
+}
+
+// null slot: conic (0,0,1), opacity 0 -> alpha = 0 < 1/255, never contributes
+__device__ __forceinline__ void rdg_init_null(Staged& sm) {
+    if (threadIdx.x < 2) {
+        sm.a[threadIdx.x][BATCH] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sm.b[threadIdx.x][BATCH] = make_float4(1.f, 0.f, 0.f, 0.f);
+        sm.c[threadIdx.x][BATCH] = make_float2(0.f, 0.f);
+    }
 }
 
 __global__ void __launch_bounds__(BATCH, 6) blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
@@ -127,11 +195,12 @@ __global__ void __launch_bounds__(BATCH, 6) blend_fwd_kernel(const uint2* __rest
                                                              const float2* __restrict__ p2, const float* __restrict__ bg,
                                                              int W, int H, int gx, float* __restrict__ out_color,
                                                              float* __restrict__ out_depth, float* __restrict__ out_alpha,
-                                                             float* __restrict__ out_T, uint32_t* __restrict__ out_ncontrib) {
+                                                             float* __restrict__ out_T, uint32_t* __restrict__ out_ncontrib,
+                                                             uint16_t* __restrict__ sub_masks) {
     __shared__ Staged sm;
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane >> 3, l8 = lane & 7;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = lane >> 3, l8 = lane & 7;
     const int sub = rdg_sub_of(warp, q);
     const int pxi = tx * RDG_TILE + 4 * (sub & 3) + (l8 & 3);
     const int py0 = ty * RDG_TILE + 4 * (sub >> 2) + 2 * (l8 >> 2), py1 = py0 + 1;
@@ -146,43 +215,67 @@ __global__ void __launch_bounds__(BATCH, 6) blend_fwd_kernel(const uint2* __rest
     float T0 = 1.0f, r0 = 0.f, g0 = 0.f, b0 = 0.f, d0 = 0.f;
     float T1 = 1.0f, r1 = 0.f, g1 = 0.f, b1 = 0.f, d1 = 0.f;
     uint32_t last0 = 0, last1 = 0;
-    const uint16_t* my_list = sm.list[sub];
 
-    for (int base = 0; base < n_g; base += BATCH) {
-        if (__syncthreads_count(done0 && done1) == BATCH) break;   // also orders the reuse of sm
-        const int idx = base + (int)threadIdx.x;
+    rdg_init_null(sm);
+    const uint32_t sa = rdg_saddr(&sm.a[0][0]), sb = rdg_saddr(&sm.b[0][0]), sc = rdg_saddr(&sm.c[0][0]);
+    const uint32_t my_list = rdg_saddr(&sm.list[sub][0]);
+    // batch 0 in flight; the id of this thread's entry of batch 1 in a register
+    uint32_t id_next = 0;
+    if (tid < n_g) {
+        const uint32_t id = vals[range.x + tid];
+        rdg_cp16(sa + tid * 16, p0 + id);
+        rdg_cp16(sb + tid * 16, p1 + id);
+        rdg_cp8(sc + tid * 8, p2 + id);
+    }
+    rdg_cp_commit();
+    if (BATCH + tid < n_g) id_next = vals[range.x + BATCH + tid];
+
+    int buf = 0;
+    for (int base = 0; base < n_g; base += BATCH, buf ^= 1) {
+        rdg_cp_wait_all();
+        const int idx = base + tid;
         unsigned m = 0u;
         if (idx < n_g) {
-            const uint32_t id = vals[range.x + idx];
-            const float4 a = p0[id], b = p1[id];
-            sm.a[threadIdx.x] = a;
-            sm.b[threadIdx.x] = b;
-            sm.c[threadIdx.x] = p2[id];
-            m = rdg_sub_mask(a, b, tile_x0, tile_y0);
+            m = rdg_sub_mask(sm.a[buf][tid], sm.b[buf][tid], tile_x0, tile_y0);
+            if (sub_masks) sub_masks[range.x + idx] = (uint16_t)m;
         }
-        sm.mask[threadIdx.x] = (uint16_t)m;
-        __syncthreads();
+        sm.mask[buf][tid] = (uint16_t)m;
+        // one barrier per batch: the copies and masks of this batch are visible, and every warp is done
+        // with the other buffer
+        if (__syncthreads_count(done0 && done1) == BATCH) {
+            // every pixel is saturated: the remaining entries still need their masks for the backward pass
+            if (sub_masks)
+                for (int k = base + BATCH + tid; k < n_g; k += BATCH) sub_masks[range.x + k] = 0;
+            break;
+        }
+        if (idx + BATCH < n_g) {
+            const uint32_t o16 = (uint32_t)((buf ^ 1) * NSLOT + tid) * 16u;
+            rdg_cp16(sa + o16, p0 + id_next);
+            rdg_cp16(sb + o16, p1 + id_next);
+            rdg_cp8(sc + (o16 >> 1), p2 + id_next);
+        }
+        rdg_cp_commit();
+        if (idx + 2 * BATCH < n_g) id_next = vals[range.x + idx + 2 * BATCH];
+
         const int cnt = min(BATCH, n_g - base);
         const unsigned act = __ballot_sync(FULL, !(done0 && done1));
         const unsigned live = ((act & 0xffu) ? 1u : 0u) | ((act & 0xff00u) ? 2u : 0u) | ((act & 0xff0000u) ? 4u : 0u) |
                               ((act & 0xff000000u) ? 8u : 0u);
         if (live == 0u) continue;                                 // this warp's 64 pixels are saturated
-        int n[4];
-        rdg_compact4<false>(sm, cnt, warp, lane, live, n);
-        const int my_n = q == 0 ? n[0] : (q == 1 ? n[1] : (q == 2 ? n[2] : n[3]));
-        const int nmax = max(max(n[0], n[1]), max(n[2], n[3]));
+        const int nmax = rdg_compact4<false>(sm, sm.mask[buf], cnt, warp, lane, live);
+        const uint32_t boff = (uint32_t)(buf * NSLOT) * 16u;
         for (int i = 0; i < nmax; ++i) {
-            const bool valid = i < my_n;
-            const int j = valid ? (int)my_list[i] : 0;
-            const float4 a = sm.a[j];
-            const float4 b = sm.b[j];
-            const float2 c = sm.c[j];
+            const uint32_t j = rdg_lds32(my_list + 4u * i) & 0xffu;
+            const uint32_t o16 = boff + (j << 4);
+            const float4 a = rdg_lds128(sa + o16);
+            const float4 b = rdg_lds128(sb + o16);
+            const float2 c = rdg_lds64(sc + (o16 >> 1));
             const float dx = a.x - pixx, dy0 = a.y - pixy0, dy1 = a.y - pixy1;
             const float Adx2 = (a.z * dx) * dx, Bdx = a.w * dx;
-            const uint32_t here = (uint32_t)(base + j + 1);
+            const uint32_t here = (uint32_t)base + j + 1u;
             float G, alpha;
             {
-                const bool on = rdg_alpha(Adx2, Bdx, b.x, dy0, b.y, G, alpha) && valid && !done0;
+                const bool on = rdg_alpha(Adx2, Bdx, b.x, dy0, b.y, G, alpha) && !done0;
                 const float test_T = T0 * (1.0f - alpha);
                 const bool stop = on && (test_T < RDG_T_STOP);    // this Gaussian is not blended; the pixel is finished
                 const bool upd = on && !stop;
@@ -196,7 +289,7 @@ __global__ void __launch_bounds__(BATCH, 6) blend_fwd_kernel(const uint2* __rest
                 last0 = upd ? here : last0;
             }
             {
-                const bool on = rdg_alpha(Adx2, Bdx, b.x, dy1, b.y, G, alpha) && valid && !done1;
+                const bool on = rdg_alpha(Adx2, Bdx, b.x, dy1, b.y, G, alpha) && !done1;
                 const float test_T = T1 * (1.0f - alpha);
                 const bool stop = on && (test_T < RDG_T_STOP);
                 const bool upd = on && !stop;
@@ -211,6 +304,7 @@ __global__ void __launch_bounds__(BATCH, 6) blend_fwd_kernel(const uint2* __rest
             }
         }
     }
+    rdg_cp_wait_all();
     const size_t hw = (size_t)H * W;
     const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
     if (in0) {
@@ -259,20 +353,31 @@ __device__ __forceinline__ void rdg_reduce_q10(const float (&v)[10], int lane, f
     r_extra = q2 + __shfl_xor_sync(FULL, q2, 1);
 }
 
+// Issue the copies of list positions pos0 - slot (slot = tid) of one backward round into buffer `buf`.
+__device__ __forceinline__ void rdg_bwd_issue(Staged& sm, uint32_t sa, uint32_t sb, uint32_t sc, int buf, int tid, uint32_t id,
+                                              const float4* p0, const float4* p1, const float2* p2) {
+    const uint32_t o16 = (uint32_t)(buf * NSLOT + tid) * 16u;
+    rdg_cp16(sa + o16, p0 + id);
+    rdg_cp16(sb + o16, p1 + id);
+    rdg_cp8(sc + (o16 >> 1), p2 + id);
+    sm.id[buf][tid] = id;
+}
+
 __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
                                                              const float4* __restrict__ p0, const float4* __restrict__ p1,
                                                              const float2* __restrict__ p2, const float* __restrict__ bg,
                                                              int W, int H, int gx, const float* __restrict__ final_T,
                                                              const uint32_t* __restrict__ n_contrib,
                                                              const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
-                                                             const float* __restrict__ dL_dalpha, float* __restrict__ acc) {
+                                                             const float* __restrict__ dL_dalpha, float* __restrict__ acc,
+                                                             const uint16_t* __restrict__ sub_masks) {
     __shared__ Staged sm;
-    __shared__ __align__(16) float pool[POOL * PREC];
+    __shared__ __align__(16) float pool[(POOL + 1) * PREC];       // + the scratch record of the null entry
     __shared__ uint32_t qlast[SUBS];
     __shared__ int wsum[NWARP];
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane >> 3, l8 = lane & 7;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = lane >> 3, l8 = lane & 7;
     const int sub = rdg_sub_of(warp, q);
     const int pxi = tx * RDG_TILE + 4 * (sub & 3) + (l8 & 3);
     const int py0 = ty * RDG_TILE + 4 * (sub >> 2) + 2 * (l8 >> 2), py1 = py0 + 1;
@@ -309,6 +414,7 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
         ql = max(ql, __shfl_xor_sync(FULL, ql, 4));
         if (l8 == 0) qlast[sub] = ql;
     }
+    rdg_init_null(sm);
     __syncthreads();
     uint32_t max_last = 0;
 #pragma unroll
@@ -321,27 +427,35 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
     // so one scalar recursion replaces the five per-channel "accumulated behind" recursions.
     float T0 = Tf0, A0 = Tf0 * (bgr * gr0 + bgg * gg0 + bgb * gb0);
     float T1 = Tf1, A1 = Tf1 * (bgr * gr1 + bgg * gg1 + bgb * gb1);
-    const int k_main = 5 * ((lane >> 2) & 1) + ((lane >> 1) & 1) + 2 * (lane & 1);
-    const int k_extra = 5 * ((lane >> 2) & 1) + 4;
+    const uint32_t sa = rdg_saddr(&sm.a[0][0]), sb = rdg_saddr(&sm.b[0][0]), sc = rdg_saddr(&sm.c[0][0]);
+    const uint32_t my_list = rdg_saddr(&sm.list[sub][0]);
+    const uint32_t pool_main = rdg_saddr(pool) + 4u * (uint32_t)(5 * ((lane >> 2) & 1) + ((lane >> 1) & 1) + 2 * (lane & 1));
+    const uint32_t pool_extra = rdg_saddr(pool) + 4u * (uint32_t)(5 * ((lane >> 2) & 1) + 4);
     const bool own_extra = (lane & 3) == 0;
-    const uint16_t* my_list = sm.list[sub];
 
-    int done_slots = 0;
+    // round r covers list positions pos = pos0 - slot, slot = 0..cnt-1 (back to front), pos0 = max_last-1-done_slots.
+    // The copies of the round that starts at done_slots + BATCH are issued while this round is blended; if
+    // the pool cut this round short they are simply issued again for the right positions.
+    int done_slots = 0, buf = 0;
+    if (tid < (int)max_last) rdg_bwd_issue(sm, sa, sb, sc, 0, tid, vals[range.x + (int)max_last - 1 - tid], p0, p1, p2);
+    rdg_cp_commit();
+    int pf_start = 0;                                              // first slot of the round sitting in (or flying into) buffer `buf`
+    uint32_t id_next = (BATCH + tid < (int)max_last) ? vals[range.x + (int)max_last - 1 - BATCH - tid] : 0u;
     while (done_slots < (int)max_last) {
-        // this round covers list positions pos = pos0 - slot, slot = 0..cnt-1 (back to front)
         const int cnt = min(BATCH, (int)max_last - done_slots);
         const int pos0 = (int)max_last - 1 - done_slots;
-        __syncthreads();                                           // previous flush is done with sm / pool
+        if (pf_start != done_slots) {                              // the previous round was cut short (uniform branch)
+            if (tid < cnt) rdg_bwd_issue(sm, sa, sb, sc, buf, tid, vals[range.x + pos0 - tid], p0, p1, p2);
+            rdg_cp_commit();
+            pf_start = done_slots;
+            id_next = (BATCH + tid < (int)max_last - done_slots) ? vals[range.x + pos0 - BATCH - tid] : 0u;
+        }
+        rdg_cp_wait_all();
         unsigned m = 0u;
-        if ((int)threadIdx.x < cnt) {
-            const uint32_t id = vals[range.x + pos0 - (int)threadIdx.x];
-            const float4 a = p0[id], b = p1[id];
-            sm.id[threadIdx.x] = id;
-            sm.a[threadIdx.x] = a;
-            sm.b[threadIdx.x] = b;
-            sm.c[threadIdx.x] = p2[id];
-            m = rdg_sub_mask(a, b, tile_x0, tile_y0);
-            const uint32_t pos = (uint32_t)(pos0 - (int)threadIdx.x);
+        if (tid < cnt) {
+            m = sub_masks ? (unsigned)sub_masks[range.x + pos0 - tid]
+                          : rdg_sub_mask(sm.a[buf][tid], sm.b[buf][tid], tile_x0, tile_y0);
+            const uint32_t pos = (uint32_t)(pos0 - tid);
 #pragma unroll
             for (int s = 0; s < SUBS; ++s)
                 if (pos >= qlast[s]) m &= ~(1u << s);
@@ -356,35 +470,36 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
             if (lane >= o) incl += t;
         }
         if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
+        __syncthreads();                                           // also: every warp is done with the previous flush
 #pragma unroll
         for (int w = 0; w < NWARP - 1; ++w)
             if (w < warp) incl += wsum[w];
-        const bool keep = ((int)threadIdx.x < cnt) && (incl <= POOL);
-        const int cnt2 = __syncthreads_count(keep);                // keep is a prefix: incl is non-decreasing
+        const bool keep = (tid < cnt) && (incl <= POOL);
         if (!keep) m = 0u;
-        sm.mask[threadIdx.x] = (uint16_t)m;
-        sm.ebase[threadIdx.x] = (uint16_t)(incl - np);
-        __syncthreads();
+        sm.mask[buf][tid] = (uint16_t)m;
+        sm.ebase[tid] = (uint16_t)(incl - np);
+        const int cnt2 = __syncthreads_count(keep);                // keep is a prefix: incl is non-decreasing
+        // next round's copies (assuming no cut) fly during the blend
+        if (done_slots + BATCH + tid < (int)max_last) rdg_bwd_issue(sm, sa, sb, sc, buf ^ 1, tid, id_next, p0, p1, p2);
+        rdg_cp_commit();
+        if (done_slots + 2 * BATCH + tid < (int)max_last) id_next = vals[range.x + pos0 - 2 * BATCH - tid];
 
-        int n[4];
-        rdg_compact4<true>(sm, cnt2, warp, lane, 0xfu, n);
-        const int my_n = q == 0 ? n[0] : (q == 1 ? n[1] : (q == 2 ? n[2] : n[3]));
-        const int nmax = max(max(n[0], n[1]), max(n[2], n[3]));
+        const int nmax = rdg_compact4<true>(sm, sm.mask[buf], cnt2, warp, lane, 0xfu);
+        const uint32_t boff = (uint32_t)(buf * NSLOT) * 16u;
         for (int i = 0; i < nmax; ++i) {
-            const bool valid = i < my_n;
-            const unsigned ent = valid ? (unsigned)my_list[i] : 0u;
-            const int j = (int)(ent & 127u);
-            const float4 a = sm.a[j];
-            const float4 b = sm.b[j];
-            const float2 c = sm.c[j];
-            const uint32_t pos = (uint32_t)(pos0 - j);
+            const uint32_t ent = rdg_lds32(my_list + 4u * i);
+            const uint32_t j = ent & 0xffu;
+            const uint32_t o16 = boff + (j << 4);
+            const float4 a = rdg_lds128(sa + o16);
+            const float4 b = rdg_lds128(sb + o16);
+            const float2 c = rdg_lds64(sc + (o16 >> 1));
+            const uint32_t pos = (uint32_t)pos0 - j;               // null slot: garbage, but its alpha test fails
             const float dx = a.x - pixx, dy0 = a.y - pixy0, dy1 = a.y - pixy1;
             const float Adx2 = (a.z * dx) * dx, Bdx = a.w * dx;
             float v[10];
             {
                 float G, alpha;
-                const bool on = rdg_alpha(Adx2, Bdx, b.x, dy0, b.y, G, alpha) && valid && (pos < last0);
+                const bool on = rdg_alpha(Adx2, Bdx, b.x, dy0, b.y, G, alpha) && (pos < last0);
                 G = on ? G : 0.0f;
                 alpha = on ? alpha : 0.0f;
                 const float inv = on ? rdg_rcp(1.0f - alpha) : 1.0f;
@@ -405,7 +520,7 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
             }
             {
                 float G, alpha;
-                const bool on = rdg_alpha(Adx2, Bdx, b.x, dy1, b.y, G, alpha) && valid && (pos < last1);
+                const bool on = rdg_alpha(Adx2, Bdx, b.x, dy1, b.y, G, alpha) && (pos < last1);
                 G = on ? G : 0.0f;
                 alpha = on ? alpha : 0.0f;
                 const float inv = on ? rdg_rcp(1.0f - alpha) : 1.0f;
@@ -425,43 +540,41 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
             }
             float r_main, r_extra;
             rdg_reduce_q10(v, lane, r_main, r_extra);
-            if (valid) {
-                float* rec = pool + (ent >> 7) * PREC;
-                rec[k_main] = r_main;
-                if (own_extra) rec[k_extra] = r_extra;
-            }
+            const uint32_t rec = ent >> 8;
+            rdg_sts32(pool_main + rec, r_main);
+            if (own_extra) rdg_sts32(pool_extra + rec, r_extra);
         }
         __syncthreads();
-        if ((int)threadIdx.x < cnt2) {
-            const int ne = __popc((unsigned)sm.mask[threadIdx.x]);
+        if (tid < cnt2) {
+            const int ne = __popc((unsigned)sm.mask[buf][tid]);
             if (ne > 0) {
-                const float4* row = reinterpret_cast<const float4*>(pool + (int)sm.ebase[threadIdx.x] * PREC);
-                float4 s0 = row[0], s1 = row[1], s2 = row[2];
+                const float2* row = reinterpret_cast<const float2*>(pool + (int)sm.ebase[tid] * PREC);
+                float2 s0 = row[0], s1 = row[1], s2 = row[2], s3 = row[3], s4 = row[4];
                 for (int k = 1; k < ne; ++k) {
-                    const float4 t0 = row[3 * k], t1 = row[3 * k + 1], t2 = row[3 * k + 2];
-                    s0.x += t0.x; s0.y += t0.y; s0.z += t0.z; s0.w += t0.w;
-                    s1.x += t1.x; s1.y += t1.y; s1.z += t1.z; s1.w += t1.w;
-                    s2.x += t2.x; s2.y += t2.y;
+                    const float2 t0 = row[5 * k], t1 = row[5 * k + 1], t2 = row[5 * k + 2], t3 = row[5 * k + 3], t4 = row[5 * k + 4];
+                    s0.x += t0.x; s0.y += t0.y; s1.x += t1.x; s1.y += t1.y; s2.x += t2.x; s2.y += t2.y;
+                    s3.x += t3.x; s3.y += t3.y; s4.x += t4.x; s4.y += t4.y;
                 }
                 // moments -> gradients: dpx = -(A Sx + B Sy), dpy = -(C Sy + B Sx), dA = -Sxx/2, dB = -Sxy, dC = -Syy/2
-                const float4 ga4 = sm.a[threadIdx.x];
-                const float cA = ga4.z, cB = ga4.w, cC = sm.b[threadIdx.x].x;
+                const float4 ga4 = sm.a[buf][tid];
+                const float cA = ga4.z, cB = ga4.w, cC = sm.b[buf][tid].x;
                 const float sx = s0.x, sy = s0.y;
-                s0.x = -(cA * sx + cB * sy);
-                s0.y = -(cC * sy + cB * sx);
-                s0.z *= -0.5f;
-                s0.w = -s0.w;
-                s1.x *= -0.5f;
-                s2.z = 0.f;
-                s2.w = 0.f;
-                float4* dst = reinterpret_cast<float4*>(acc + (size_t)sm.id[threadIdx.x] * NACC);
-                atomicAdd(dst + 0, s0);
-                atomicAdd(dst + 1, s1);
-                atomicAdd(dst + 2, s2);
+                const float4 o0 = make_float4(-(cA * sx + cB * sy), -(cC * sy + cB * sx), -0.5f * s1.x, -s1.y);
+                const float4 o1 = make_float4(-0.5f * s2.x, s2.y, s3.x, s3.y);
+                const float4 o2 = make_float4(s4.x, s4.y, 0.f, 0.f);
+                float4* dst = reinterpret_cast<float4*>(acc + (size_t)sm.id[buf][tid] * NACC);
+                atomicAdd(dst + 0, o0);
+                atomicAdd(dst + 1, o1);
+                atomicAdd(dst + 2, o2);
             }
         }
         done_slots += cnt2;
+        if (cnt2 == cnt) {                                         // the prefetched round is the next one
+            pf_start = done_slots;
+            buf ^= 1;
+        }
     }
+    rdg_cp_wait_all();
 }
 
 static bool rdg_use_v1() {
@@ -479,7 +592,8 @@ extern "C" int rdg_blend_fwd(int64_t n, const RdgGeom* geom, const RdgBins* bins
     const int gx = (W + RDG_TILE - 1) / RDG_TILE, gy = (H + RDG_TILE - 1) / RDG_TILE;
     blend_fwd_kernel<<<gx * gy, BATCH, 0, (cudaStream_t)stream>>>(
         (const uint2*)bins->ranges, bins->vals_sorted, (const float4*)geom->p0, (const float4*)geom->p1,
-        (const float2*)geom->p2, view->bg, W, H, gx, out->color, out->depth, out->alpha, out->final_T, out->n_contrib);
+        (const float2*)geom->p2, view->bg, W, H, gx, out->color, out->depth, out->alpha, out->final_T, out->n_contrib,
+        bins->sub_masks);
     RDG_CHECK_LAUNCH();
     rdg_count_launches(1);
     return RDG_OK;
@@ -495,7 +609,8 @@ extern "C" int rdg_blend_bwd(int64_t n, const RdgGeom* geom, const RdgBins* bins
     const int gx = (W + RDG_TILE - 1) / RDG_TILE, gy = (H + RDG_TILE - 1) / RDG_TILE;
     blend_bwd_kernel<<<gx * gy, BATCH, 0, (cudaStream_t)stream>>>(
         (const uint2*)bins->ranges, bins->vals_sorted, (const float4*)geom->p0, (const float4*)geom->p1,
-        (const float2*)geom->p2, view->bg, W, H, gx, fwd->final_T, fwd->n_contrib, dL_dcolor, dL_ddepth, dL_dalpha, acc);
+        (const float2*)geom->p2, view->bg, W, H, gx, fwd->final_T, fwd->n_contrib, dL_dcolor, dL_ddepth, dL_dalpha, acc,
+        bins->sub_masks);
     RDG_CHECK_LAUNCH();
     rdg_count_launches(1);
     return RDG_OK;

@@ -4,16 +4,23 @@
 // against /root/reference/src/utils/loss_utils.py by tests/golden/losses.npz.
 //
 // SSIM: 11-tap separable Gaussian (sigma 1.5, zero padding 5, per channel).  Pass 1
-// blurs (x, y, x^2, y^2, xy) of a 16x16 tile from a 26x26 halo in shared memory, forms
+// blurs (x, y, x^2, y^2, xy) of a 32x32 tile from a 42x42 halo in shared memory, forms
 // the SSIM map and its three partial-derivative maps; pass 2 blurs those maps and
-// applies the chain rule.  HBM-bound: 24 B/px read + 36 B/px maps written, then
-// 36 + 24 B/px read + 12 B/px written (the reference's conv2d chain moves ~700 B/px).
+// applies the chain rule.  24 B/px read + 36 B/px maps written, then 36 + 24 B/px read +
+// 12 B/px written (the reference's conv2d chain moves ~700 B/px).  The global Pearson
+// depth statistics and the alpha regulariser ride on the channel-0 CTAs of pass 1, their
+// gradients on pass 2, so the whole loss stage is three launches.
 #include <math.h>
 #include "common.cuh"
 
-#define LT 16            // output tile
+#define ST 32                  // output tile: ST x ST pixels per CTA and channel
 #define HALO 5
-#define LH (LT + 2 * HALO)  // 26
+#define SHL (ST + 2 * HALO)    // 42: halo tile edge
+#define IPITCH 43              // halo-tile row pitch; odd, so 32 consecutive rows at one column hit 32 banks
+#define HPITCH 33              // row pitch of the horizontally blurred planes
+#define LTHREADS 256
+#define SEG 8                  // outputs per thread, horizontal pass (sliding window of SEG + 10 inputs in registers)
+#define VSEG 4                 // outputs per thread, vertical pass
 
 // /root/reference/src/utils/loss_utils.py:34-41: float32 taps exp(-(i-5)^2 / (2*1.5^2)) / sum,
 // evaluated the way the reference does (torch.Tensor of Python floats, divided by its float32 sum).
@@ -21,120 +28,248 @@ __constant__ float c_taps[11] = {1.028380124e-03f, 7.598758209e-03f, 3.600077331
                                  2.130055279e-01f, 2.660117149e-01f, 2.130055279e-01f, 1.093606874e-01f,
                                  3.600077331e-02f, 7.598758209e-03f, 1.028380124e-03f};
 
-template <int Q>
-__device__ __forceinline__ void blur_tile(float (*halo)[LH][LH + 1], float (*hz)[LH][LT], float* out) {
-    // horizontal: LH rows x LT cols
-    for (int idx = threadIdx.x; idx < LH * LT; idx += RDG_BLOCK) {
-        const int r = idx / LT, c = idx % LT;
+// Header of the loss workspace (256 bytes reserved): running sums and the Pearson gradient coefficients.
+struct LossHdr {
+    double sums[8];   // 0 ssim, 1 |x-y|, 2..6 depth: sum p, g, pp, gg, pg, 7 sum(1 - alpha)
+    float coef[8];    // 0 mean g, 1 mean p, 2 d/d(g - mg), 3 d/d(p - mp)  (dL/ddepth = c2 (g-mg) + c3 (p-mp)), 4 dL/dalpha
+};
+
+// Separable 11-tap blur of an SHL x SHL halo tile down to ST x ST, register-tiled: the horizontal pass
+// gives every thread one row and SEG adjacent outputs (each input is loaded once and used for up to 11
+// taps x NQ planes from registers), the vertical pass one column and VSEG outputs.  12 FMA per shared-memory
+// load instead of 1 - the first version of this kernel was LSU bound (ncu r01).
+template <int NQ>
+__device__ __forceinline__ void blur_vertical(const float (*hz)[SHL][HPITCH], int c, int vs, float (&o)[NQ][VSEG]) {
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            float s = 0.f;
+    for (int q = 0; q < NQ; ++q)
 #pragma unroll
-            for (int k = 0; k < 11; ++k) s = __fmaf_rn(c_taps[k], halo[q][r][c + k], s);
-            hz[q][r][c] = s;
+        for (int i = 0; i < VSEG; ++i) o[q][i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < VSEG + 10; ++k) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const float v = hz[q][vs * VSEG + k][c];
+#pragma unroll
+            for (int i = 0; i < VSEG; ++i) {
+                const int tap = k - i;
+                if (tap >= 0 && tap <= 10) o[q][i] = __fmaf_rn(c_taps[tap], v, o[q][i]);
+            }
         }
-    }
-    __syncthreads();
-    const int r = threadIdx.x / LT, c = threadIdx.x % LT;
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < 11; ++k) s = __fmaf_rn(c_taps[k], hz[q][r + k][c], s);
-        out[q] = s;
     }
 }
 
-__global__ void __launch_bounds__(RDG_BLOCK) ssim_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
-                                                             int H, int W, float* __restrict__ map_mu,
-                                                             float* __restrict__ map_s1, float* __restrict__ map_s12,
-                                                             double* __restrict__ sums) {
-    __shared__ float halo[5][LH][LH + 1];
-    __shared__ float hz[5][LH][LT];
-    __shared__ float red[2][RDG_BLOCK / 32];
+__global__ void __launch_bounds__(LTHREADS) ssim_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                            int H, int W, float* __restrict__ map_mu,
+                                                            float* __restrict__ map_s1, float* __restrict__ map_s12,
+                                                            LossHdr* __restrict__ hdr, const float* __restrict__ depth,
+                                                            const float* __restrict__ gt_depth, const float* __restrict__ alpha) {
+    __shared__ float in[2][SHL][IPITCH];
+    __shared__ float hz[5][SHL][HPITCH];
+    __shared__ double red[8][LTHREADS / 32];
     const int ch = blockIdx.z;
     const size_t plane = (size_t)ch * H * W;
-    const int x0 = blockIdx.x * LT - HALO, y0 = blockIdx.y * LT - HALO;
-    for (int idx = threadIdx.x; idx < LH * LH; idx += RDG_BLOCK) {
-        const int r = idx / LH, c = idx % LH;
+    const int x0 = blockIdx.x * ST - HALO, y0 = blockIdx.y * ST - HALO;
+    for (int idx = threadIdx.x; idx < SHL * SHL; idx += LTHREADS) {
+        const int r = idx / SHL, c = idx % SHL;
         const int y = y0 + r, x = x0 + c;
         float a = 0.f, b = 0.f;
         if (x >= 0 && x < W && y >= 0 && y < H) { a = pred[plane + (size_t)y * W + x]; b = gt[plane + (size_t)y * W + x]; }
-        halo[0][r][c] = a; halo[1][r][c] = b; halo[2][r][c] = a * a; halo[3][r][c] = b * b; halo[4][r][c] = a * b;
+        in[0][r][c] = a;
+        in[1][r][c] = b;
     }
     __syncthreads();
-    float o[5];
-    blur_tile<5>(halo, hz, o);
-    const int r = threadIdx.x / LT, c = threadIdx.x % LT;
-    const int y = blockIdx.y * LT + r, x = blockIdx.x * LT + c;
-    float ssim_v = 0.f, l1_v = 0.f;
-    if (x < W && y < H) {
-        const float mu1 = o[0], mu2 = o[1];
-        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
-        const float s1 = o[2] - mu1_sq, s2 = o[3] - mu2_sq, s12 = o[4] - mu12;
-        const float C1 = 0.0001f, C2 = 0.0009f;
-        const float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2, B1 = mu1_sq + mu2_sq + C1, B2 = s1 + s2 + C2;
-        const float inv = 1.0f / (B1 * B2);
-        ssim_v = A1 * A2 * inv;
-        // partial derivatives of the map w.r.t. (mu1 | E[x^2] | E[xy]) held independent
-        const float d_s1 = -A1 * A2 * inv / B2;
-        const float d_s12 = 2.f * A1 * inv;
-        const float d_mu = (2.f * mu2 * B1 - A1 * 2.f * mu1) / (B1 * B1) * (A2 / B2) + d_s1 * (-2.f * mu1) + d_s12 * (-mu2);
-        const size_t pix = plane + (size_t)y * W + x;
-        if (map_mu) { map_mu[pix] = d_mu; map_s1[pix] = d_s1; map_s12[pix] = d_s12; }
-        l1_v = fabsf(halo[0][r + HALO][c + HALO] - halo[1][r + HALO][c + HALO]);
+    if (threadIdx.x < SHL * (ST / SEG)) {
+        const int r = threadIdx.x % SHL, s = threadIdx.x / SHL;
+        float a[5][SEG];
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) a[q][i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < SEG + 10; ++k) {
+            const float xv = in[0][r][s * SEG + k], yv = in[1][r][s * SEG + k];
+            const float xx = xv * xv, yy = yv * yv, xy = xv * yv;
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) {
+                const int tap = k - i;
+                if (tap >= 0 && tap <= 10) {
+                    const float w = c_taps[tap];
+                    a[0][i] = __fmaf_rn(w, xv, a[0][i]);
+                    a[1][i] = __fmaf_rn(w, yv, a[1][i]);
+                    a[2][i] = __fmaf_rn(w, xx, a[2][i]);
+                    a[3][i] = __fmaf_rn(w, yy, a[3][i]);
+                    a[4][i] = __fmaf_rn(w, xy, a[4][i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) hz[q][r][s * SEG + i] = a[q][i];
     }
+    __syncthreads();
+    const int c = threadIdx.x % ST, vs = threadIdx.x / ST;
+    float o[5][VSEG];
+    blur_vertical<5>(hz, c, vs, o);
+    const int x = blockIdx.x * ST + c;
+    float ssim_v = 0.f, l1_v = 0.f;
+    double st[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < VSEG; ++i) {
+        const int y = blockIdx.y * ST + vs * VSEG + i;
+        if (x < W && y < H) {
+            const float mu1 = o[0][i], mu2 = o[1][i];
+            const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+            const float s1 = o[2][i] - mu1_sq, s2 = o[3][i] - mu2_sq, s12 = o[4][i] - mu12;
+            const float C1 = 0.0001f, C2 = 0.0009f;
+            const float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2, B1 = mu1_sq + mu2_sq + C1, B2 = s1 + s2 + C2;
+            const float inv = 1.0f / (B1 * B2);
+            ssim_v += A1 * A2 * inv;
+            const size_t hwpix = (size_t)y * W + x;
+            if (map_mu) {
+                // partial derivatives of the map w.r.t. (mu1 | E[x^2] | E[xy]) held independent
+                const float d_s1 = -A1 * A2 * inv / B2;
+                const float d_s12 = 2.f * A1 * inv;
+                const float d_mu = (2.f * mu2 * B1 - A1 * 2.f * mu1) / (B1 * B1) * (A2 / B2) + d_s1 * (-2.f * mu1) + d_s12 * (-mu2);
+                map_mu[plane + hwpix] = d_mu;
+                map_s1[plane + hwpix] = d_s1;
+                map_s12[plane + hwpix] = d_s12;
+            }
+            const int r = vs * VSEG + i + HALO;
+            l1_v += fabsf(in[0][r][c + HALO] - in[1][r][c + HALO]);
+            if (ch == 0) {
+                if (depth) {
+                    const double p = depth[hwpix], g = gt_depth[hwpix];
+                    st[0] += p; st[1] += g; st[2] += p * p; st[3] += g * g; st[4] += p * g;
+                }
+                if (alpha) st[5] += (double)(1.0f - alpha[hwpix]);
+            }
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     ssim_v = warp_sum(ssim_v);
     l1_v = warp_sum(l1_v);
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ssim_v; red[1][threadIdx.x >> 5] = l1_v; }
+    if (lane == 0) { red[0][warp] = ssim_v; red[1][warp] = l1_v; }
+    const bool extras = ch == 0 && (depth || alpha);
+    if (extras) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) st[k] += __shfl_xor_sync(0xffffffffu, st[k], off);
+            if (lane == 0) red[2 + k][warp] = st[k];
+        }
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float a = 0.f, b = 0.f;
-        for (int k = 0; k < RDG_BLOCK / 32; ++k) { a += red[0][k]; b += red[1][k]; }
-        atomicAdd(&sums[0], (double)a);
-        atomicAdd(&sums[1], (double)b);
+    if (threadIdx.x < (extras ? 8 : 2)) {
+        double t = 0;
+        for (int w = 0; w < LTHREADS / 32; ++w) t += red[threadIdx.x][w];
+        atomicAdd(&hdr->sums[threadIdx.x], t);
     }
 }
 
-__global__ void __launch_bounds__(RDG_BLOCK) ssim_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
-                                                             int H, int W, const float* __restrict__ map_mu,
-                                                             const float* __restrict__ map_s1, const float* __restrict__ map_s12,
-                                                             float k_ssim, float k_l1, float* __restrict__ dL_dpred) {
-    __shared__ float halo[3][LH][LH + 1];
-    __shared__ float hz[3][LH][LT];
+__global__ void __launch_bounds__(LTHREADS) ssim_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                            int H, int W, const float* __restrict__ map_mu,
+                                                            const float* __restrict__ map_s1, const float* __restrict__ map_s12,
+                                                            float k_ssim, float k_l1, float* __restrict__ dL_dpred,
+                                                            const LossHdr* __restrict__ hdr, const float* __restrict__ depth,
+                                                            const float* __restrict__ gt_depth, float* __restrict__ dL_ddepth,
+                                                            float* __restrict__ dL_dalpha) {
+    __shared__ float in[3][SHL][IPITCH];
+    __shared__ float hz[3][SHL][HPITCH];
     const int ch = blockIdx.z;
     const size_t plane = (size_t)ch * H * W;
-    const int x0 = blockIdx.x * LT - HALO, y0 = blockIdx.y * LT - HALO;
-    for (int idx = threadIdx.x; idx < LH * LH; idx += RDG_BLOCK) {
-        const int r = idx / LH, c = idx % LH;
+    const int x0 = blockIdx.x * ST - HALO, y0 = blockIdx.y * ST - HALO;
+    for (int idx = threadIdx.x; idx < SHL * SHL; idx += LTHREADS) {
+        const int r = idx / SHL, c = idx % SHL;
         const int y = y0 + r, x = x0 + c;
         float a = 0.f, b = 0.f, d = 0.f;
         if (x >= 0 && x < W && y >= 0 && y < H) {
             const size_t pix = plane + (size_t)y * W + x;
             a = map_mu[pix]; b = map_s1[pix]; d = map_s12[pix];
         }
-        halo[0][r][c] = a; halo[1][r][c] = b; halo[2][r][c] = d;
+        in[0][r][c] = a; in[1][r][c] = b; in[2][r][c] = d;
     }
     __syncthreads();
-    float o[3];
-    blur_tile<3>(halo, hz, o);
-    const int r = threadIdx.x / LT, c = threadIdx.x % LT;
-    const int y = blockIdx.y * LT + r, x = blockIdx.x * LT + c;
-    if (x < W && y < H) {
-        const size_t pix = plane + (size_t)y * W + x;
-        const float xv = pred[pix], yv = gt[pix];
-        const float dssim = o[0] + 2.f * xv * o[1] + yv * o[2];
-        const float diff = xv - yv;
-        const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-        dL_dpred[pix] = k_ssim * dssim + k_l1 * sgn;
+    if (threadIdx.x < SHL * (ST / SEG)) {
+        const int r = threadIdx.x % SHL, s = threadIdx.x / SHL;
+        float a[3][SEG];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) a[q][i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < SEG + 10; ++k) {
+            const float v0 = in[0][r][s * SEG + k], v1 = in[1][r][s * SEG + k], v2 = in[2][r][s * SEG + k];
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) {
+                const int tap = k - i;
+                if (tap >= 0 && tap <= 10) {
+                    const float w = c_taps[tap];
+                    a[0][i] = __fmaf_rn(w, v0, a[0][i]);
+                    a[1][i] = __fmaf_rn(w, v1, a[1][i]);
+                    a[2][i] = __fmaf_rn(w, v2, a[2][i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) hz[q][r][s * SEG + i] = a[q][i];
+    }
+    __syncthreads();
+    const int c = threadIdx.x % ST, vs = threadIdx.x / ST;
+    float o[3][VSEG];
+    blur_vertical<3>(hz, c, vs, o);
+    const int x = blockIdx.x * ST + c;
+    const bool do_depth = ch == 0 && dL_ddepth != nullptr, do_alpha = ch == 0 && dL_dalpha != nullptr;
+    float mg = 0.f, mp = 0.f, cg = 0.f, cp = 0.f, ca = 0.f;
+    if (do_depth) { mg = hdr->coef[0]; mp = hdr->coef[1]; cg = hdr->coef[2]; cp = hdr->coef[3]; }
+    if (do_alpha) ca = hdr->coef[4];
+#pragma unroll
+    for (int i = 0; i < VSEG; ++i) {
+        const int y = blockIdx.y * ST + vs * VSEG + i;
+        if (x < W && y < H) {
+            const size_t hwpix = (size_t)y * W + x, pix = plane + hwpix;
+            const float xv = pred[pix], yv = gt[pix];
+            const float dssim = o[0][i] + 2.f * xv * o[1][i] + yv * o[2][i];
+            const float diff = xv - yv;
+            const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+            dL_dpred[pix] = k_ssim * dssim + k_l1 * sgn;
+            if (do_depth) dL_ddepth[hwpix] = cg * (gt_depth[hwpix] - mg) + cp * (depth[hwpix] - mp);
+            if (do_alpha) dL_dalpha[hwpix] = ca;
+        }
     }
 }
 
-__global__ void loss_finalize_kernel(const double* __restrict__ sums, double n, float w_l1, float w_dssim, float* __restrict__ out) {
+// sums -> losses (+ the coefficients of the Pearson / alpha gradients for the second pass)
+__global__ void loss_finalize_kernel(LossHdr* __restrict__ hdr, double n, double npix, float w_l1, float w_dssim,
+                                     int use_depth, float w_pearson, float eps, int use_alpha, float w_alpha,
+                                     float* __restrict__ out) {
+    const double* sums = hdr->sums;
     const double ssim = sums[0] / n, l1 = sums[1] / n;
     out[0] = (float)(w_l1 * l1 + w_dssim * (1.0 - ssim));
     out[1] = (float)l1;
     out[2] = (float)ssim;
+    if (use_depth) {
+        // loss_utils.py:100-117: 1 - mean(z_p * z_g), z = (v - mean) / (std_unbiased + eps)
+        const double m = npix;
+        const double mp = sums[2] / m, mg = sums[3] / m;
+        const double varp = fmax((sums[4] - m * mp * mp) / (m - 1.0), 0.0), varg = fmax((sums[5] - m * mg * mg) / (m - 1.0), 0.0);
+        const double sp = sqrt(varp), sg = sqrt(varg);
+        const double a = sp + (double)eps, b = sg + (double)eps;
+        const double spg = sums[6] - m * mp * mg;
+        out[3] = (float)(1.0 - spg / (m * a * b));
+        const double k1 = 1.0 / (m * a * b);
+        const double k2 = sp > 0.0 ? spg / (m * a * a * b) / ((m - 1.0) * sp) : 0.0;
+        hdr->coef[0] = (float)mg;
+        hdr->coef[1] = (float)mp;
+        hdr->coef[2] = (float)(-(double)w_pearson * k1);
+        hdr->coef[3] = (float)((double)w_pearson * k2);
+    }
+    if (use_alpha) {
+        out[4] = (float)((double)w_alpha * sums[7] / npix);
+        hdr->coef[4] = (float)(-(double)w_alpha / npix);
+    }
 }
 
 extern "C" int64_t rdg_l1_dssim_workspace_bytes(int32_t channels, int32_t height, int32_t width) {
@@ -142,34 +277,49 @@ extern "C" int64_t rdg_l1_dssim_workspace_bytes(int32_t channels, int32_t height
     return 256 + (int64_t)3 * channels * height * width * (int64_t)sizeof(float);
 }
 
-extern "C" int rdg_l1_dssim(const float* pred, const float* gt, int32_t channels, int32_t height, int32_t width,
-                            float w_l1, float w_dssim, float* out_loss, float* dL_dpred,
-                            void* workspace, int64_t workspace_bytes, void* stream) {
+extern "C" int rdg_losses(const float* pred, const float* gt, int32_t channels, int32_t height, int32_t width,
+                          float w_l1, float w_dssim, const RdgLossTerms* extra, float* out_loss, float* dL_dpred,
+                          void* workspace, int64_t workspace_bytes, void* stream) {
     RDG_CHECK_ARG(pred && gt && out_loss && workspace, "null argument");
     RDG_CHECK_ARG(channels > 0 && height > 0 && width > 0, "empty image");
     if (workspace_bytes < rdg_l1_dssim_workspace_bytes(channels, height, width)) {
-        rdg_set_error("rdg_l1_dssim: workspace too small");
+        rdg_set_error("rdg_losses: workspace too small");
         return RDG_E_CAPACITY;
     }
+    const bool use_depth = extra && extra->depth && extra->gt_depth && extra->w_pearson != 0.0f;
+    const bool use_alpha = extra && extra->alpha && extra->w_alpha != 0.0f;
     cudaStream_t s = (cudaStream_t)stream;
-    double* sums = (double*)workspace;
+    LossHdr* hdr = (LossHdr*)workspace;
     const size_t plane = (size_t)channels * height * width;
     float* maps = (float*)((char*)workspace + 256);
-    RDG_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), s));
-    const dim3 grid((width + LT - 1) / LT, (height + LT - 1) / LT, channels);
+    RDG_CUDA(cudaMemsetAsync(hdr, 0, sizeof(LossHdr), s));
+    const dim3 grid((width + ST - 1) / ST, (height + ST - 1) / ST, channels);
     const bool need_grad = dL_dpred != nullptr;
-    ssim_fwd_kernel<<<grid, RDG_BLOCK, 0, s>>>(pred, gt, height, width, need_grad ? maps : nullptr,
-                                              need_grad ? maps + plane : nullptr, need_grad ? maps + 2 * plane : nullptr, sums);
+    ssim_fwd_kernel<<<grid, LTHREADS, 0, s>>>(pred, gt, height, width, need_grad ? maps : nullptr,
+                                             need_grad ? maps + plane : nullptr, need_grad ? maps + 2 * plane : nullptr, hdr,
+                                             use_depth ? extra->depth : nullptr, use_depth ? extra->gt_depth : nullptr,
+                                             use_alpha ? extra->alpha : nullptr);
     RDG_CHECK_LAUNCH();
-    const double n = (double)plane;
-    loss_finalize_kernel<<<1, 1, 0, s>>>(sums, n, w_l1, w_dssim, out_loss);
+    const double n = (double)plane, npix = (double)height * (double)width;
+    loss_finalize_kernel<<<1, 1, 0, s>>>(hdr, n, npix, w_l1, w_dssim, use_depth ? 1 : 0, use_depth ? extra->w_pearson : 0.f,
+                                         use_depth ? extra->pearson_eps : 0.f, use_alpha ? 1 : 0,
+                                         use_alpha ? extra->w_alpha : 0.f, out_loss);
     if (need_grad) {
-        ssim_bwd_kernel<<<grid, RDG_BLOCK, 0, s>>>(pred, gt, height, width, maps, maps + plane, maps + 2 * plane,
-                                                  (float)(-(double)w_dssim / n), (float)((double)w_l1 / n), dL_dpred);
+        ssim_bwd_kernel<<<grid, LTHREADS, 0, s>>>(pred, gt, height, width, maps, maps + plane, maps + 2 * plane,
+                                                 (float)(-(double)w_dssim / n), (float)((double)w_l1 / n), dL_dpred, hdr,
+                                                 use_depth ? extra->depth : nullptr, use_depth ? extra->gt_depth : nullptr,
+                                                 use_depth ? extra->dL_ddepth : nullptr, use_alpha ? extra->dL_dalpha : nullptr);
     }
     RDG_CHECK_LAUNCH();
     rdg_count_launches(need_grad ? 3 : 2);
     return RDG_OK;
+}
+
+extern "C" int rdg_l1_dssim(const float* pred, const float* gt, int32_t channels, int32_t height, int32_t width,
+                            float w_l1, float w_dssim, float* out_loss, float* dL_dpred,
+                            void* workspace, int64_t workspace_bytes, void* stream) {
+    return rdg_losses(pred, gt, channels, height, width, w_l1, w_dssim, nullptr, out_loss, dL_dpred, workspace,
+                      workspace_bytes, stream);
 }
 
 // ------------------------------------------------------------------ Pearson ----

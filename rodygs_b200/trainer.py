@@ -108,10 +108,6 @@ class SplatTrainStep:
         lib = _lib.load()
         self._ws_bytes = int(lib.rdg_l1_dssim_workspace_bytes(3, self.H, self.W))
         self._loss_ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.dev)
-        self._pearson_box = torch.tensor([[0, 0, self.H, self.W]], dtype=torch.int32, device=self.dev)
-        self._pearson_w = torch.tensor([self.w[2]], **f32)
-        self._pearson_stats = torch.zeros(8, dtype=torch.float64, device=self.dev)
-        self._pearson_out = torch.zeros(1, **f32)
         self.last_state: Optional[engine.FwdState] = None
         self.stage_events = None   # set by enable_stage_timing()
 
@@ -178,17 +174,17 @@ class SplatTrainStep:
             return None
         # ---- losses + their gradients w.r.t. the rendered maps (fused kernels) ----
         w_l1, w_ds, w_p, w_a = self.w
-        self.loss_parts.zero_()
-        check(lib.rdg_l1_dssim(ptr(color), ptr(gt_image), 3, self.H, self.W, w_l1, w_ds, ptr(self.loss_parts),
-                               ptr(self.dL_dcolor), ptr(self._loss_ws), self._ws_bytes, stream))
         use_depth = w_p != 0.0 and gt_depth is not None
-        if use_depth:
-            self.dL_ddepth.zero_()
-            check(lib.rdg_pearson(ptr(depth), ptr(gt_depth), self.H, self.W, ptr(self._pearson_box), ptr(self._pearson_w), 1,
-                                  1e-6, self.loss_parts[3:4].data_ptr(), ptr(self.dL_ddepth), ptr(self._pearson_stats), stream))
         use_alpha = w_a != 0.0
+        terms = _lib.RdgLossTerms()
+        if use_depth:
+            terms.depth, terms.gt_depth, terms.dL_ddepth = ptr(depth), ptr(gt_depth), ptr(self.dL_ddepth)
+            terms.w_pearson, terms.pearson_eps = w_p, 1e-6
         if use_alpha:
-            check(lib.rdg_alpha_reg(ptr(alpha), self.H * self.W, w_a, self.loss_parts[4:5].data_ptr(), ptr(self.dL_dalpha), stream))
+            terms.alpha, terms.dL_dalpha, terms.w_alpha = ptr(alpha), ptr(self.dL_dalpha), w_a
+        # loss_parts[0:5] are written by the finalize kernel; disabled terms keep their zero
+        check(lib.rdg_losses(ptr(color), ptr(gt_image), 3, self.H, self.W, w_l1, w_ds, C.byref(terms), ptr(self.loss_parts),
+                             ptr(self.dL_dcolor), ptr(self._loss_ws), self._ws_bytes, stream))
         self._mark("loss")
         # ---- backward ----
         target = self.grads

@@ -347,6 +347,55 @@ def test_losses_match_oracle():
     assert abs(lc.item() - lr.item()) < 2e-6
     assert helpers.rel_err(dc.grad.cpu(), dr.grad) < GRAD_TOL
 
+@pytest.mark.gpu
+def test_fused_loss_stage_matches_oracle():
+    """rdg_losses: photometric + global Pearson + alpha regulariser in three launches (the trainer's loss stage)."""
+    import ctypes as C
+    from oracle import loss_oracle as lo
+    from rodygs_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    for (H, W) in ((33, 70), (128, 96), (97, 131)):
+        a = torch.rand(3, H, W, generator=g)
+        b = (a + 0.1 * torch.randn(3, H, W, generator=g)).clamp(0, 1)
+        d1 = torch.rand(1, H, W, generator=g) * 5 + 1
+        d2 = d1 * 0.7 + torch.rand(1, H, W, generator=g)
+        al = torch.rand(1, H, W, generator=g)
+        w_p, w_a = 0.05, 0.01
+        ar, dr, alr = a.clone().requires_grad_(True), d1.clone().requires_grad_(True), al.clone().requires_grad_(True)
+        photo = lo.photometric(ar, b)
+        pear = lo.pearson_depth(dr, d2)
+        areg = w_a * (1.0 - alr).mean()
+        (photo + w_p * pear + areg).backward()
+        dev = "cuda"
+        ac, bc, dc, d2c, alc = a.to(dev), b.to(dev), d1.to(dev), d2.to(dev), al.to(dev)
+        out = torch.zeros(8, device=dev)
+        gcol = torch.empty(3, H, W, device=dev)
+        gdep = torch.full((1, H, W), 7.0, device=dev)
+        galp = torch.full((1, H, W), 7.0, device=dev)
+        ws_bytes = int(lib.rdg_l1_dssim_workspace_bytes(3, H, W))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        terms = _lib.RdgLossTerms()
+        terms.depth, terms.gt_depth, terms.dL_ddepth = dc.data_ptr(), d2c.data_ptr(), gdep.data_ptr()
+        terms.w_pearson, terms.pearson_eps = w_p, 1e-6
+        terms.alpha, terms.dL_dalpha, terms.w_alpha = alc.data_ptr(), galp.data_ptr(), w_a
+        for _ in range(2):   # twice: the workspace header is reset by the call itself
+            _lib.check(lib.rdg_losses(ac.data_ptr(), bc.data_ptr(), 3, H, W, 0.8, 0.2, C.byref(terms), out.data_ptr(),
+                                      gcol.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr()))
+        o = out.cpu()
+        assert abs(o[0].item() - photo.item()) < 2e-6
+        assert abs(o[1].item() - lo.l1(a, b).item()) < 1e-6 and abs(o[2].item() - lo.ssim(a, b).item()) < 2e-6
+        assert abs(o[3].item() - pear.item()) < 2e-6
+        assert abs(o[4].item() - areg.item()) < 1e-7
+        assert helpers.rel_err(gcol.cpu(), ar.grad) < GRAD_TOL
+        assert helpers.rel_err(gdep.cpu(), dr.grad) < GRAD_TOL
+        assert helpers.rel_err(galp.cpu(), alr.grad) < 1e-6
+        # terms switched off: only the photometric entries are written
+        out2 = torch.full((8,), -1.0, device=dev)
+        _lib.check(lib.rdg_losses(ac.data_ptr(), bc.data_ptr(), 3, H, W, 0.8, 0.2, None, out2.data_ptr(),
+                                  gcol.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr()))
+        assert abs(out2[0].item() - photo.item()) < 2e-6 and out2[3].item() == -1.0 and out2[4].item() == -1.0
+
 
 def test_sync_free_mode_matches_and_reports_overflow():
     H, W, n = 64, 64, 1500
