@@ -119,6 +119,9 @@ typedef struct RdgBins {
     uint32_t* num_rendered;  /* [2]: [0] = D (sum tiles_touched), [1] = 1 if D > D_cap (nothing past D_cap is written) */
     uint64_t* keys_unsorted; /* optional [D_cap] for tests; NULL to use workspace */
     uint32_t* vals_unsorted; /* optional [D_cap] */
+    uint16_t* sub_masks;     /* optional [D_cap]: rdg_blend_fwd stores, per sorted instance, the 16-bit mask of the
+                              * 4x4-pixel sub-tiles the Gaussian can reach; rdg_blend_bwd reads it back (NULL:
+                              * the backward pass recomputes it) */
 } RdgBins;
 
 typedef struct RdgImage {

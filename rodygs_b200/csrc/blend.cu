@@ -35,10 +35,10 @@
 #define BATCH 128               // list entries staged per round == threads per CTA
 #define NWARP (BATCH / 32)
 #define NSLOT (BATCH + 1)       // + the null slot (opacity 0) that pads the lists
-#define LROW (BATCH + 1)        // list row stride (u32): rows of neighbouring sub-tiles start in different banks
+#define LROW (BATCH + 2)        // list row stride (u16): rows of neighbouring sub-tiles start in different banks
 #define POOL 512                // (sub-tile, entry) gradient records per round (backward)
 #define PREC 10                 // floats per record
-#define NULL_ENTRY ((uint32_t)BATCH | ((uint32_t)(POOL * PREC * 4) << 8))   // null slot, scratch record
+#define NULL_ENTRY ((uint16_t)BATCH)   // null slot (its ebase points at the scratch record), rank 0
 #define FULL 0xffffffffu
 
 extern "C" int rdg_blend_fwd_v1(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view, const RdgImage* out, void* stream);
@@ -49,10 +49,9 @@ struct __align__(16) Staged {
     float4 a[2][NSLOT];           // px, py, A, B          (double buffered: batch k+1 lands while batch k is blended)
     float4 b[2][NSLOT];           // C, opacity, r, g
     float2 c[2][NSLOT];           // b, depth
-    uint32_t id[2][BATCH];
     uint16_t mask[2][BATCH];      // bit s: may touch sub-tile s (s = 4 * sub_y + sub_x)
-    uint16_t ebase[BATCH];        // backward: first gradient record of this entry
-    uint32_t list[SUBS][LROW];    // per sub-tile compacted entries: slot | (record byte offset << 8)
+    uint16_t ebase[NSLOT];        // backward: first gradient record of this entry
+    uint16_t list[SUBS][LROW];    // per sub-tile compacted entries: slot | (rank of the sub-tile among the entry's << 8)
 };
 
 __device__ __forceinline__ float rdg_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -62,9 +61,9 @@ __device__ __forceinline__ float rdg_sqrt(float x) { float y; asm("sqrt.approx.f
 // shared-window accesses by 32-bit address: the inner loops index three arrays with one offset
 // and keep the window bases in registers
 __device__ __forceinline__ uint32_t rdg_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t rdg_lds32(uint32_t addr) {
+__device__ __forceinline__ uint32_t rdg_lds16(uint32_t addr) {
     uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ float2 rdg_lds64(uint32_t addr) {
@@ -150,7 +149,8 @@ __device__ __forceinline__ int rdg_sub_of(int warp, int q) { return (2 * (warp >
 
 // Build the lists of this warp's four quarters from mask[0..cnt) (order preserved) and pad them to a
 // common length with the null entry.  live: bit q set = quarter q still has work.  WITH_E: append the
-// byte offset of the entry's gradient record.  Returns the common length.
+// rank of the sub-tile among the entry's sub-tiles (its gradient record is ebase[slot] + rank).
+// Returns the common length.
 template <bool WITH_E>
 __device__ __forceinline__ int rdg_compact4(Staged& sm, const uint16_t* mask, int cnt, int warp, int lane, unsigned live) {
     int n[4] = {0, 0, 0, 0};
@@ -158,7 +158,6 @@ __device__ __forceinline__ int rdg_compact4(Staged& sm, const uint16_t* mask, in
     for (int g = 0; g * 32 < cnt; ++g) {
         const int j = g * 32 + lane;
         const unsigned m = (j < cnt) ? (unsigned)mask[j] : 0u;
-        const unsigned eb = WITH_E ? (unsigned)sm.ebase[j] : 0u;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int s = rdg_sub_of(warp, q);
@@ -166,8 +165,8 @@ __device__ __forceinline__ int rdg_compact4(Staged& sm, const uint16_t* mask, in
             const unsigned bal = __ballot_sync(FULL, bit);
             if (bit) {
                 unsigned e = (unsigned)j;
-                if (WITH_E) e |= ((eb + __popc(m & ((1u << s) - 1u))) * (PREC * 4)) << 8;
-                sm.list[s][n[q] + __popc(bal & lt)] = e;
+                if (WITH_E) e |= (unsigned)__popc(m & ((1u << s) - 1u)) << 8;
+                sm.list[s][n[q] + __popc(bal & lt)] = (uint16_t)e;
             }
             n[q] += __popc(bal);
         }
@@ -175,7 +174,7 @@ __device__ __forceinline__ int rdg_compact4(Staged& sm, const uint16_t* mask, in
     const int nmax = max(max(n[0], n[1]), max(n[2], n[3]));
     const int q = lane >> 3;
     const int my_n = q == 0 ? n[0] : (q == 1 ? n[1] : (q == 2 ? n[2] : n[3]));
-    uint32_t* row = sm.list[rdg_sub_of(warp, q)];
+    uint16_t* row = sm.list[rdg_sub_of(warp, q)];
     for (int k = my_n + (lane & 7); k < nmax; k += 8) row[k] = NULL_ENTRY;
     __syncwarp();
     return nmax;
@@ -187,6 +186,7 @@ __device__ __forceinline__ void rdg_init_null(Staged& sm) {
         sm.a[threadIdx.x][BATCH] = make_float4(0.f, 0.f, 0.f, 0.f);
         sm.b[threadIdx.x][BATCH] = make_float4(1.f, 0.f, 0.f, 0.f);
         sm.c[threadIdx.x][BATCH] = make_float2(0.f, 0.f);
+        sm.ebase[BATCH] = (uint16_t)POOL;
     }
 }
 
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(BATCH, 6) blend_fwd_kernel(const uint2* __rest
         const int nmax = rdg_compact4<false>(sm, sm.mask[buf], cnt, warp, lane, live);
         const uint32_t boff = (uint32_t)(buf * NSLOT) * 16u;
         for (int i = 0; i < nmax; ++i) {
-            const uint32_t j = rdg_lds32(my_list + 4u * i) & 0xffu;
+            const uint32_t j = rdg_lds16(my_list + 2u * i);
             const uint32_t o16 = boff + (j << 4);
             const float4 a = rdg_lds128(sa + o16);
             const float4 b = rdg_lds128(sb + o16);
@@ -354,13 +354,12 @@ __device__ __forceinline__ void rdg_reduce_q10(const float (&v)[10], int lane, f
 }
 
 // Issue the copies of list positions pos0 - slot (slot = tid) of one backward round into buffer `buf`.
-__device__ __forceinline__ void rdg_bwd_issue(Staged& sm, uint32_t sa, uint32_t sb, uint32_t sc, int buf, int tid, uint32_t id,
+__device__ __forceinline__ void rdg_bwd_issue(uint32_t sa, uint32_t sb, uint32_t sc, int buf, int tid, uint32_t id,
                                               const float4* p0, const float4* p1, const float2* p2) {
     const uint32_t o16 = (uint32_t)(buf * NSLOT + tid) * 16u;
     rdg_cp16(sa + o16, p0 + id);
     rdg_cp16(sb + o16, p1 + id);
     rdg_cp8(sc + (o16 >> 1), p2 + id);
-    sm.id[buf][tid] = id;
 }
 
 __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
@@ -432,12 +431,13 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
     const uint32_t pool_main = rdg_saddr(pool) + 4u * (uint32_t)(5 * ((lane >> 2) & 1) + ((lane >> 1) & 1) + 2 * (lane & 1));
     const uint32_t pool_extra = rdg_saddr(pool) + 4u * (uint32_t)(5 * ((lane >> 2) & 1) + 4);
     const bool own_extra = (lane & 3) == 0;
+    const uint32_t sebase = rdg_saddr(&sm.ebase[0]);
 
     // round r covers list positions pos = pos0 - slot, slot = 0..cnt-1 (back to front), pos0 = max_last-1-done_slots.
     // The copies of the round that starts at done_slots + BATCH are issued while this round is blended; if
     // the pool cut this round short they are simply issued again for the right positions.
     int done_slots = 0, buf = 0;
-    if (tid < (int)max_last) rdg_bwd_issue(sm, sa, sb, sc, 0, tid, vals[range.x + (int)max_last - 1 - tid], p0, p1, p2);
+    if (tid < (int)max_last) rdg_bwd_issue(sa, sb, sc, 0, tid, vals[range.x + (int)max_last - 1 - tid], p0, p1, p2);
     rdg_cp_commit();
     int pf_start = 0;                                              // first slot of the round sitting in (or flying into) buffer `buf`
     uint32_t id_next = (BATCH + tid < (int)max_last) ? vals[range.x + (int)max_last - 1 - BATCH - tid] : 0u;
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
         const int cnt = min(BATCH, (int)max_last - done_slots);
         const int pos0 = (int)max_last - 1 - done_slots;
         if (pf_start != done_slots) {                              // the previous round was cut short (uniform branch)
-            if (tid < cnt) rdg_bwd_issue(sm, sa, sb, sc, buf, tid, vals[range.x + pos0 - tid], p0, p1, p2);
+            if (tid < cnt) rdg_bwd_issue(sa, sb, sc, buf, tid, vals[range.x + pos0 - tid], p0, p1, p2);
             rdg_cp_commit();
             pf_start = done_slots;
             id_next = (BATCH + tid < (int)max_last - done_slots) ? vals[range.x + pos0 - BATCH - tid] : 0u;
@@ -480,19 +480,20 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
         sm.ebase[tid] = (uint16_t)(incl - np);
         const int cnt2 = __syncthreads_count(keep);                // keep is a prefix: incl is non-decreasing
         // next round's copies (assuming no cut) fly during the blend
-        if (done_slots + BATCH + tid < (int)max_last) rdg_bwd_issue(sm, sa, sb, sc, buf ^ 1, tid, id_next, p0, p1, p2);
+        if (done_slots + BATCH + tid < (int)max_last) rdg_bwd_issue(sa, sb, sc, buf ^ 1, tid, id_next, p0, p1, p2);
         rdg_cp_commit();
         if (done_slots + 2 * BATCH + tid < (int)max_last) id_next = vals[range.x + pos0 - 2 * BATCH - tid];
 
         const int nmax = rdg_compact4<true>(sm, sm.mask[buf], cnt2, warp, lane, 0xfu);
         const uint32_t boff = (uint32_t)(buf * NSLOT) * 16u;
         for (int i = 0; i < nmax; ++i) {
-            const uint32_t ent = rdg_lds32(my_list + 4u * i);
+            const uint32_t ent = rdg_lds16(my_list + 2u * i);
             const uint32_t j = ent & 0xffu;
             const uint32_t o16 = boff + (j << 4);
             const float4 a = rdg_lds128(sa + o16);
             const float4 b = rdg_lds128(sb + o16);
             const float2 c = rdg_lds64(sc + (o16 >> 1));
+            const uint32_t rec = (rdg_lds16(sebase + 2u * j) + (ent >> 8)) * (uint32_t)(PREC * 4);
             const uint32_t pos = (uint32_t)pos0 - j;               // null slot: garbage, but its alpha test fails
             const float dx = a.x - pixx, dy0 = a.y - pixy0, dy1 = a.y - pixy1;
             const float Adx2 = (a.z * dx) * dx, Bdx = a.w * dx;
@@ -540,7 +541,6 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
             }
             float r_main, r_extra;
             rdg_reduce_q10(v, lane, r_main, r_extra);
-            const uint32_t rec = ent >> 8;
             rdg_sts32(pool_main + rec, r_main);
             if (own_extra) rdg_sts32(pool_extra + rec, r_extra);
         }
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
                 const float4 o0 = make_float4(-(cA * sx + cB * sy), -(cC * sy + cB * sx), -0.5f * s1.x, -s1.y);
                 const float4 o1 = make_float4(-0.5f * s2.x, s2.y, s3.x, s3.y);
                 const float4 o2 = make_float4(s4.x, s4.y, 0.f, 0.f);
-                float4* dst = reinterpret_cast<float4*>(acc + (size_t)sm.id[buf][tid] * NACC);
+                float4* dst = reinterpret_cast<float4*>(acc + (size_t)vals[range.x + pos0 - tid] * NACC);
                 atomicAdd(dst + 0, o0);
                 atomicAdd(dst + 1, o1);
                 atomicAdd(dst + 2, o2);

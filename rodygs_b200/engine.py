@@ -276,11 +276,13 @@ def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = T
         want_keys = config.emit_sorted_keys or not use_tiles
         keys = torch.empty(d_cap, dtype=torch.int64, device=dev) if want_keys else None
         vals = torch.empty(d_cap, dtype=torch.int32, device=dev)
+        sub_masks = torch.empty(d_cap, dtype=torch.int16, device=dev) if keep_for_backward else None
         ws_bytes = int((lib.rdg_bin_tiles_workspace_bytes if use_tiles else lib.rdg_bin_workspace_bytes)(n, d_cap, H, W))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         bins = RdgBins()
         bins.keys_sorted, bins.vals_sorted = ptr(keys), ptr(vals)
         bins.ranges, bins.point_offsets, bins.num_rendered = ptr(ranges), ptr(point_offsets), ptr(num_rendered)
+        bins.sub_masks = ptr(sub_masks)
         if config.debug_keep_unsorted:
             extras["keys_unsorted"] = torch.empty(d_cap, dtype=torch.int64, device=dev)
             extras["vals_unsorted"] = torch.empty(d_cap, dtype=torch.int32, device=dev)
@@ -314,7 +316,7 @@ def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = T
     if stage_hook:
         stage_hook("blend_fwd")
 
-    extras.update({"keys_sorted": keys, "point_offsets": point_offsets})
+    extras.update({"keys_sorted": keys, "point_offsets": point_offsets, "sub_masks": sub_masks})
     state = FwdState(scene=scene, view=view, n=n, geom=geom, vals_sorted=vals, ranges=ranges,
                      num_rendered=num_rendered, final_T=final_T, n_contrib=n_contrib, d_cap=d_cap, extras=extras)
     return color, depth, alpha, geom["radii"], state
@@ -362,6 +364,7 @@ def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: Sce
     sc_s, vw_s, gm_s = _scene_struct(state.scene), _view_struct(state.view), _geom_struct(state.geom)
     bins = RdgBins()
     bins.vals_sorted, bins.ranges, bins.num_rendered = ptr(state.vals_sorted), ptr(state.ranges), ptr(state.num_rendered)
+    bins.sub_masks = ptr(state.extras.get("sub_masks"))
     img = RdgImage()
     img.final_T, img.n_contrib = ptr(state.final_T), ptr(state.n_contrib)
 
