@@ -264,8 +264,10 @@ __global__ void __launch_bounds__(BATCH, 6) blend_fwd_kernel(const uint2* __rest
         if (live == 0u) continue;                                 // this warp's 64 pixels are saturated
         const int nmax = rdg_compact4<false>(sm, sm.mask[buf], cnt, warp, lane, live);
         const uint32_t boff = (uint32_t)(buf * NSLOT) * 16u;
+        uint32_t j_next = rdg_lds16(my_list);
         for (int i = 0; i < nmax; ++i) {
-            const uint32_t j = rdg_lds16(my_list + 2u * i);
+            const uint32_t j = j_next;
+            j_next = rdg_lds16(my_list + 2u * (i + 1));            // one entry ahead (rows are padded): off the critical path
             const uint32_t o16 = boff + (j << 4);
             const float4 a = rdg_lds128(sa + o16);
             const float4 b = rdg_lds128(sb + o16);
@@ -437,7 +439,8 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
     // The copies of the round that starts at done_slots + BATCH are issued while this round is blended; if
     // the pool cut this round short they are simply issued again for the right positions.
     int done_slots = 0, buf = 0;
-    if (tid < (int)max_last) rdg_bwd_issue(sa, sb, sc, 0, tid, vals[range.x + (int)max_last - 1 - tid], p0, p1, p2);
+    uint32_t id_cur = (tid < (int)max_last) ? vals[range.x + (int)max_last - 1 - tid] : 0u;   // this thread's entry of the round
+    if (tid < (int)max_last) rdg_bwd_issue(sa, sb, sc, 0, tid, id_cur, p0, p1, p2);
     rdg_cp_commit();
     int pf_start = 0;                                              // first slot of the round sitting in (or flying into) buffer `buf`
     uint32_t id_next = (BATCH + tid < (int)max_last) ? vals[range.x + (int)max_last - 1 - BATCH - tid] : 0u;
@@ -445,7 +448,8 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
         const int cnt = min(BATCH, (int)max_last - done_slots);
         const int pos0 = (int)max_last - 1 - done_slots;
         if (pf_start != done_slots) {                              // the previous round was cut short (uniform branch)
-            if (tid < cnt) rdg_bwd_issue(sa, sb, sc, buf, tid, vals[range.x + pos0 - tid], p0, p1, p2);
+            id_cur = (tid < cnt) ? vals[range.x + pos0 - tid] : 0u;
+            if (tid < cnt) rdg_bwd_issue(sa, sb, sc, buf, tid, id_cur, p0, p1, p2);
             rdg_cp_commit();
             pf_start = done_slots;
             id_next = (BATCH + tid < (int)max_last - done_slots) ? vals[range.x + pos0 - BATCH - tid] : 0u;
@@ -482,12 +486,15 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
         // next round's copies (assuming no cut) fly during the blend
         if (done_slots + BATCH + tid < (int)max_last) rdg_bwd_issue(sa, sb, sc, buf ^ 1, tid, id_next, p0, p1, p2);
         rdg_cp_commit();
+        const uint32_t id_pf = id_next;
         if (done_slots + 2 * BATCH + tid < (int)max_last) id_next = vals[range.x + pos0 - 2 * BATCH - tid];
 
         const int nmax = rdg_compact4<true>(sm, sm.mask[buf], cnt2, warp, lane, 0xfu);
         const uint32_t boff = (uint32_t)(buf * NSLOT) * 16u;
+        uint32_t ent_next = rdg_lds16(my_list);
         for (int i = 0; i < nmax; ++i) {
-            const uint32_t ent = rdg_lds16(my_list + 2u * i);
+            const uint32_t ent = ent_next;
+            ent_next = rdg_lds16(my_list + 2u * (i + 1));          // one entry ahead (rows are padded): off the critical path
             const uint32_t j = ent & 0xffu;
             const uint32_t o16 = boff + (j << 4);
             const float4 a = rdg_lds128(sa + o16);
@@ -562,7 +569,7 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
                 const float4 o0 = make_float4(-(cA * sx + cB * sy), -(cC * sy + cB * sx), -0.5f * s1.x, -s1.y);
                 const float4 o1 = make_float4(-0.5f * s2.x, s2.y, s3.x, s3.y);
                 const float4 o2 = make_float4(s4.x, s4.y, 0.f, 0.f);
-                float4* dst = reinterpret_cast<float4*>(acc + (size_t)vals[range.x + pos0 - tid] * NACC);
+                float4* dst = reinterpret_cast<float4*>(acc + (size_t)id_cur * NACC);
                 atomicAdd(dst + 0, o0);
                 atomicAdd(dst + 1, o1);
                 atomicAdd(dst + 2, o2);
@@ -572,6 +579,7 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
         if (cnt2 == cnt) {                                         // the prefetched round is the next one
             pf_start = done_slots;
             buf ^= 1;
+            id_cur = id_pf;
         }
     }
     rdg_cp_wait_all();

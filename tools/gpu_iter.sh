@@ -28,6 +28,25 @@ if [ -n "$EXTRA_BENCH" ]; then
   timeout 900 python bench.py $EXTRA_BENCH --no-cpu-baseline > gpurun_out/bench_extra.log 2>&1; echo "exit $?" >> gpurun_out/bench_extra.log
   summ gpurun_out/bench_extra.log
 fi
+if [ -n "$LAUNCH_LIST" ]; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${LL_S:-0} -c ${LL_C:-400} --csv --log-file gpurun_out/launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
+  python - <<'PY'
+import csv, collections
+lines=[l for l in open('gpurun_out/launches.csv') if not l.startswith('==')]
+rows=list(csv.DictReader(lines))
+def us(r):
+    v=float(r['Metric Value'].replace(',','')); u=r['Metric Unit']
+    return v/1e3 if u=='ns' else (v*1e3 if u=='ms' else v)
+# last full step: from the last preprocess_fwd launch to the end... print the tail sequence
+names=[r['Kernel Name'][:50] for r in rows]
+idx=[i for i,n in enumerate(names) if 'preprocess_fwd' in n]
+if len(idx)>=2:
+    a,b=idx[-2],idx[-1]
+    tot=sum(us(r) for r in rows[a:b])
+    print('one step (launch order), total %.1f us over %d launches'%(tot,b-a))
+    for r in rows[a:b]: print('  %-50s %8.1f us'%(r['Kernel Name'][:50],us(r)))
+PY
+fi
 if [ -n "$NCU_K" ]; then
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$NCU_K" -s ${NCU_S:-12} -c ${NCU_C:-2} -o gpurun_out/prof_k -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_k.log 2>&1
   echo "ncu exit $?"
