@@ -229,6 +229,17 @@ def run_ours(args, rank, world, local_rank):
     h2d_bytes = sum(t.numel() * 4 for t in (st_vm, st_pm, st_bt, st_gt, st_gtd))
     d2h_bytes = host_loss.numel() * 4
 
+    # data-parallel exchange (world > 1): the ranks all-gather the 12-byte factors of dL/dSH and all-reduce the rest;
+    # every rank needs the view matrix and B(t) of every rank's view of the step (rank-major order)
+    factored = world > 1 and not args.plain_allreduce and not args.forward_only
+    all_vm, all_bt = [], []
+    if factored:
+        step.enable_factored_exchange(views_per_rank=1, world_size=world)
+        for j in range(len(my_views)):
+            cs = [synthetic.make_camera(r + j * world, n_views, H, W, T) for r in range(world)]
+            all_vm.append(torch.stack([c.world_view_transform.t().contiguous() for c in cs]).to(dev).contiguous())
+            all_bt.append(torch.stack([step.p("table")[c.time_index] for c in cs]).contiguous())
+
     adam_state = None
     if args.adam:
         adam_state = (torch.zeros_like(step.params), torch.zeros_like(step.params))
@@ -259,11 +270,16 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.current_stream().wait_event(ready[k % 2])
             prefetch(k + 1)
             vm, pm, bt, gt, gtd = slots[k % 2]
-        step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, bt, gt, gtd, forward_only=args.forward_only)
+        step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, bt, gt, gtd, forward_only=args.forward_only,
+                              dcolor_slot=0 if factored else None)
         if e2e:
             consumed[k % 2].record()
         if world > 1:
-            step.allreduce_grads(1.0 / world)
+            if args.plain_allreduce:
+                step.allreduce_grads(1.0 / world)
+            else:
+                j = k % len(dev_inputs)
+                step.exchange_grads(all_vm[j], all_bt[j])
         if adam_state is not None:
             it_count[0] += 1
             _lib.check(lib.rdg_adam(step.params.data_ptr(), step.grads.data_ptr(), adam_state[0].data_ptr(),
@@ -368,7 +384,9 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": workload_name(args.config), "n_gaussians": N, "visible": V, "duplicates": D,
                        "pixels": P, "views_per_step": world, "l2": "inputs larger than L2 (params+SH 472 MB, sort buffers)",
                        "optimizer": "fused Adam in the timed region" if args.adam else "excluded (metric = raster fwd+bwd+loss)",
-                       "sync_free": True, "parallelism": f"dp{world} (view-sharded, allreduce of flat grads)"},
+                       "sync_free": True, "parallelism": (f"dp{world} (view-sharded; all-gather of the 12 B/Gaussian factors of dL/dSH + allreduce of "
+                                       "the other gradients, dL/dSH rebuilt per rank)" if factored else
+                                       f"dp{world} (view-sharded, allreduce of the flat gradient buffer)")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
@@ -396,6 +414,8 @@ def main():
     ap.add_argument("--adam", action="store_true")
     ap.add_argument("--forward-only", action="store_true", help="BASELINE config 5: inference render sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--plain-allreduce", action="store_true",
+                    help="N>1: all-reduce the whole flat gradient buffer instead of the factored SH exchange (A/B)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -147,6 +147,9 @@ typedef struct RdgSceneGrad {
     float* table;            /* [T,num_basis,7] accumulated (+=) */
     float* basis_t;          /* [num_basis,7]   accumulated (+=) */
     float* g7_scratch;       /* [n_dynamic,8] scratch, required when scene.frame_order is set */
+    float* dcolor;           /* optional [N,3]: dL/d(rgb) of every Gaussian after the SH clamp mask (zeros when it is not
+                              * visible) - the 12-byte factors from which rdg_sh_grad_views rebuilds dL/dSH of all views
+                              * of a data-parallel step; pass st/dy.sh_dc = sh_rest = NULL with it to skip the dSH rows */
 } RdgSceneGrad;
 
 int rdg_abi_version(void);
@@ -192,6 +195,15 @@ int rdg_blend_bwd(int64_t n, const RdgGeom* geom, const RdgBins* bins, const Rdg
 /* acc -> parameter gradients (+ pose, + deformation) (§8 a10, App. A.7). */
 int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, const RdgGeom* geom,
                        const float* acc, const RdgSceneGrad* grads, void* stream);
+
+/* dL/dSH of all views of a data-parallel step from its rank-1 factors: for every Gaussian
+ *   dL/dSH[k][c] = scale * sum_v Y_k(normalize(x(t_v) - campos_v)) * dcolor[v][c],
+ * with x(t_v) the (deformed, scene.raw) mean at view v's time.  viewmatrices [V,16] glm storage, basis_ts [V,K,7]
+ * (B(t_v), needed when scene.use_deform), dcolor [V,N,3] as written by rdg_preprocess_bwd through
+ * RdgSceneGrad.dcolor (gathered from all ranks).  Overwrites grad_*->sh_dc / sh_rest; V <= 16. */
+int rdg_sh_grad_views(const RdgScene* scene, int32_t sh_degree, int32_t n_views, const float* viewmatrices,
+                      const float* basis_ts, const float* dcolor, float scale, const RdgSetGrad* grad_static,
+                      const RdgSetGrad* grad_dynamic, void* stream);
 
 /* ---- losses ----------------------------------------------------------------- */
 

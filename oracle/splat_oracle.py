@@ -95,6 +95,28 @@ def sh_to_rgb(deg: int, sh: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
     return res
 
 
+def sh_basis(deg: int, dirs: torch.Tensor) -> torch.Tensor:
+    """Y_k(dir) for k < (deg+1)^2 as [M,K]: the coefficients sh_to_rgb multiplies (sh_utils.py:72-101)."""
+    K = (deg + 1) ** 2
+    eye = torch.eye(K, dtype=dirs.dtype)
+    cols = [sh_to_rgb(deg, eye[k].reshape(1, K, 1).expand(dirs.shape[0], K, 3), dirs)[:, 0] for k in range(K)]
+    return torch.stack(cols, 1)
+
+
+def sh_grad_from_factors(deg: int, means_per_view, campos_per_view, dcolor_per_view) -> torch.Tensor:
+    """dL/dSH [N,16,3] of several views from its rank-1 factors (the data-parallel exchange of
+    rodygs_b200/csrc/sh_grad_views.cu): sum_v Y_k(normalize(x_v - campos_v)) * dcolor_v[c], where dcolor_v is
+    dL/d(rgb) after the clamp mask (zero for Gaussians that view v does not see)."""
+    n = means_per_view[0].shape[0]
+    K = (deg + 1) ** 2
+    g = torch.zeros(n, 16, 3, dtype=means_per_view[0].dtype)
+    for x, cp, dc in zip(means_per_view, campos_per_view, dcolor_per_view):
+        d = x - cp.reshape(1, 3)
+        d = d / d.norm(dim=1, keepdim=True)
+        g[:, :K] += sh_basis(deg, d).unsqueeze(2) * dc.unsqueeze(1)
+    return g
+
+
 class Preprocessed(NamedTuple):
     idx: torch.Tensor          # [M] global ids of Gaussians in front of the near plane
     visible: torch.Tensor      # [M] bool (survived det / empty-rect culls)

@@ -57,7 +57,8 @@ class RdgSetGrad(C.Structure):
 
 class RdgSceneGrad(C.Structure):
     _fields_ = [("st", RdgSetGrad), ("dy", RdgSetGrad), ("colors_precomp", c_ptr), ("means2D", c_ptr),
-                ("viewmatrix", c_ptr), ("motion_coeff", c_ptr), ("table", c_ptr), ("basis_t", c_ptr), ("g7_scratch", c_ptr)]
+                ("viewmatrix", c_ptr), ("motion_coeff", c_ptr), ("table", c_ptr), ("basis_t", c_ptr), ("g7_scratch", c_ptr),
+                ("dcolor", c_ptr)]
 
 
 class RdgLossTerms(C.Structure):
@@ -84,6 +85,8 @@ SYMBOLS = {
                                 C.POINTER(RdgImage), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "rdg_preprocess_bwd": (C.c_int, [C.POINTER(RdgScene), C.POINTER(RdgView), C.POINTER(RdgGeom), c_ptr,
                                      C.POINTER(RdgSceneGrad), c_ptr]),
+    "rdg_sh_grad_views": (C.c_int, [C.POINTER(RdgScene), C.c_int32, C.c_int32, c_ptr, c_ptr, c_ptr, C.c_float,
+                                    C.POINTER(RdgSetGrad), C.POINTER(RdgSetGrad), c_ptr]),
     "rdg_l1_dssim_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "rdg_l1_dssim": (C.c_int, [c_ptr, c_ptr, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, c_ptr, c_ptr,
                                c_ptr, C.c_int64, c_ptr]),

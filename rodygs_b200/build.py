@@ -32,6 +32,7 @@ SOURCES = {
     "blend.cu": [],
     "blend_v1.cu": [],
     "preprocess_bwd.cu": [],
+    "sh_grad_views.cu": [],
     "loss.cu": [],
 }
 HEADERS = ["common.cuh", "scene.cuh", os.path.join("..", "..", "include", "rodygs_b200.h")]

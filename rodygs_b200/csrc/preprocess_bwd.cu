@@ -268,6 +268,12 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
             for (int k = 0; k < SH_ROW; ++k) my_sh[k] = 0.f;
         }
 
+        // factors of dL/dSH for the data-parallel exchange (rdg_sh_grad_views): dL/d(rgb) after the clamp mask
+        if (valid && p.gr.dcolor) {
+            float* o = p.gr.dcolor + i * 3;
+            o[0] = vis ? grgb[0] : 0.f; o[1] = vis ? grgb[1] : 0.f; o[2] = vis ? grgb[2] : 0.f;
+        }
+
         // ---- through the activations / deformation, and write out ----
         float g7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         bool has_def = false;

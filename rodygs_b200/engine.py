@@ -344,6 +344,7 @@ class SceneGrads:
     table: Optional[torch.Tensor] = None        # must be zero-initialised
     basis_t: Optional[torch.Tensor] = None      # must be zero-initialised
     g7_scratch: Optional[torch.Tensor] = None   # [nd,8] scratch (allocated on demand)
+    dcolor: Optional[torch.Tensor] = None       # [N,3] factors of dL/dSH for the data-parallel exchange
 
 
 def _setgrad_struct(g: SetGrads) -> RdgSetGrad:
@@ -380,6 +381,7 @@ def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: Sce
     g.st, g.dy = _setgrad_struct(grads.st), _setgrad_struct(grads.dy)
     g.colors_precomp, g.means2D, g.viewmatrix = ptr(grads.colors_precomp), ptr(grads.means2D), ptr(grads.viewmatrix)
     g.motion_coeff, g.table, g.basis_t = ptr(grads.motion_coeff), ptr(grads.table), ptr(grads.basis_t)
+    g.dcolor = ptr(grads.dcolor)
     if state.scene.use_deform and state.scene.frame_order is not None and grads.table is not None:
         if grads.g7_scratch is None:
             grads.g7_scratch = torch.empty(state.scene.motion_coeff.shape[0], 8, dtype=torch.float32, device=dev)

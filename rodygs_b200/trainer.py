@@ -25,26 +25,36 @@ PARAM_ORDER = ("xyz", "scaling", "rotation", "opacity", "features_dc", "features
 
 def flat_layout(n_static: int, n_dynamic: int, num_basis: int, num_times: int) -> Tuple[Dict[str, Tuple[int, Tuple[int, ...]]], int]:
     """name -> (float offset, shape) of every trainable tensor inside the flat buffer.
-    Offsets are multiples of 64 floats (256 B) so that every slice is vector-aligned."""
+    Offsets are multiples of 64 floats (256 B) so that every slice is vector-aligned.  The SH blocks
+    come last: everything before `sh_start(layout)` is what the data-parallel step all-reduces,
+    the SH gradients are rebuilt from their 12-byte factors (see SplatTrainStep.exchange_grads)."""
     shapes = {}
     for tag, n in (("static", n_static), ("dynamic", n_dynamic)):
         shapes[f"{tag}.xyz"] = (n, 3)
         shapes[f"{tag}.scaling"] = (n, 3)
         shapes[f"{tag}.rotation"] = (n, 4)
         shapes[f"{tag}.opacity"] = (n, 1)
-        shapes[f"{tag}.features_dc"] = (n, 1, 3)
-        shapes[f"{tag}.features_rest"] = (n, 15, 3)
     shapes["motion_coeff"] = (n_dynamic, 1, num_basis)
     shapes["table"] = (num_times, num_basis, 7)
     shapes["basis_t"] = (num_basis, 7)
+    sh_shapes = {}
+    for tag, n in (("static", n_static), ("dynamic", n_dynamic)):
+        sh_shapes[f"{tag}.features_dc"] = (n, 1, 3)
+        sh_shapes[f"{tag}.features_rest"] = (n, 15, 3)
     layout, off = {}, 0
-    for name, shp in shapes.items():
-        numel = 1
-        for s in shp:
-            numel *= s
-        layout[name] = (off, shp)
-        off += (numel + 63) // 64 * 64
+    for group in (shapes, sh_shapes):
+        for name, shp in group.items():
+            numel = 1
+            for s in shp:
+                numel *= s
+            layout[name] = (off, shp)
+            off += (numel + 63) // 64 * 64
     return layout, off
+
+
+def sh_start(layout) -> int:
+    """Float offset of the first SH block inside the flat buffer (= length of the all-reduced range)."""
+    return layout["static.features_dc"][0]
 
 
 def shard_views(n_views: int, world_size: int, rank: int) -> List[int]:
@@ -53,15 +63,30 @@ def shard_views(n_views: int, world_size: int, rank: int) -> List[int]:
 
 
 def allreduce_flat(buf: torch.Tensor, scale: Optional[float] = None, group=None) -> torch.Tensor:
-    """The data path's only exchange step: in-place sum of the flat gradient buffer over the
-    data-parallel group (NCCL on GPUs, gloo in the CPU tests), then an optional scale
-    (1 / views for a mean over the step's views)."""
+    """The data path's exchange step for a flat gradient range: in-place sum over the data-parallel group
+    (NCCL on GPUs, gloo in the CPU tests), then an optional scale (1 / views for a mean over the step's
+    views).  On NCCL a scale of exactly 1 / world_size rides on the collective (ReduceOp.AVG) instead of a
+    second pass over the buffer."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        if buf.is_cuda and scale is not None and abs(scale * world - 1.0) < 1e-12:
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=group)
+            return buf
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     if scale is not None and scale != 1.0:
         buf.mul_(scale)
     return buf
+
+
+def allgather_rows(local: torch.Tensor, out: torch.Tensor, group=None) -> torch.Tensor:
+    """out[rank * k : (rank + 1) * k] = local[0:k] of every rank (k = local.shape[0]); a copy when there is one rank."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_gather_into_tensor(out, local, group=group)
+    else:
+        out.copy_(local)
+    return out
 
 
 class SplatTrainStep:
@@ -152,9 +177,11 @@ class SplatTrainStep:
     # -- one view --------------------------------------------------------------------------------
     def forward_backward(self, viewmatrix: torch.Tensor, projmatrix: torch.Tensor, tanfovx: float, tanfovy: float,
                          basis_t: torch.Tensor, gt_image: torch.Tensor, gt_depth: Optional[torch.Tensor],
-                         accumulate: bool = False, forward_only: bool = False):
+                         accumulate: bool = False, forward_only: bool = False, dcolor_slot: Optional[int] = None):
         """viewmatrix / projmatrix in glm storage (V^T, P^T).  Gradients land in self.grads
         (overwritten unless accumulate=True, in which case a second flat buffer is summed in).
+        dcolor_slot: data-parallel mode - do not write dL/dSH; write its 12-byte factors dL/d(rgb) into
+        self.dcolor_local[dcolor_slot] instead (exchange_grads() rebuilds dL/dSH of all views from them).
         Returns self.loss_parts (device tensor; no host sync)."""
         lib = _lib.load()
         stream = _lib.stream_ptr()
@@ -198,7 +225,12 @@ class SplatTrainStep:
             self.view_grad.zero_()
             self.g("table").zero_()
             self.g("basis_t").zero_()
-            grads = SceneGrads(st=self._setgrad("static"), dy=self._setgrad("dynamic"), means2D=self.means2D_grad,
+            gst, gdy = self._setgrad("static"), self._setgrad("dynamic")
+            dcolor = None
+            if dcolor_slot is not None:
+                gst.sh_dc = gst.sh_rest = gdy.sh_dc = gdy.sh_rest = None
+                dcolor = self.dcolor_local[dcolor_slot]
+            grads = SceneGrads(st=gst, dy=gdy, means2D=self.means2D_grad, dcolor=dcolor,
                                viewmatrix=self.view_grad,
                                motion_coeff=self.g("motion_coeff").view(self.nd, self.num_basis) if deform else None,
                                table=self.g("table") if deform else None, basis_t=self.g("basis_t") if deform else None,
@@ -212,8 +244,43 @@ class SplatTrainStep:
         return self.loss_parts
 
     def allreduce_grads(self, scale: Optional[float] = None):
-        """Sum (and optionally scale) the flat gradient buffer over the data-parallel group."""
+        """Sum (and optionally scale) the WHOLE flat gradient buffer over the data-parallel group
+        (the plain exchange; exchange_grads() is the one that scales)."""
         allreduce_flat(self.grads, scale, self.pg)
+
+    # -- data-parallel exchange with factored SH gradients -----------------------------------------
+    def enable_factored_exchange(self, views_per_rank: int, world_size: int):
+        """Buffers for exchange_grads(): the local factors [views_per_rank, N, 3] and the gathered ones."""
+        n = self.ns + self.nd
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.views_per_rank, self.world_size = int(views_per_rank), int(world_size)
+        self.dcolor_local = torch.zeros(self.views_per_rank, n, 3, **f32)
+        self.dcolor_all = torch.zeros(self.views_per_rank * self.world_size, n, 3, **f32)
+
+    def exchange_grads(self, viewmats_all: torch.Tensor, basis_all: torch.Tensor):
+        """Finish a data-parallel step whose local views ran with dcolor_slot=0..views_per_rank-1:
+        all-gather the 12-byte factors of dL/dSH (81 % of the gradient message as 192-byte blocks),
+        all-reduce everything else, rebuild dL/dSH of ALL views from the factors (rdg_sh_grad_views).
+        viewmats_all [V,4,4] glm storage and basis_all [V,K,7] in rank-major view order (rank r holds views
+        r*views_per_rank ..); the result in self.grads is the mean over the V views."""
+        lib = _lib.load()
+        v_total = self.views_per_rank * self.world_size
+        n_plain = sh_start(self.layout)
+        allgather_rows(self.dcolor_local, self.dcolor_all, self.pg)
+        allreduce_flat(self.grads[:n_plain], 1.0 / self.world_size, self.pg)
+        if self.views_per_rank > 1:
+            self.grads[:n_plain].mul_(1.0 / self.views_per_rank)
+        deform = self.nd > 0
+        scene = SceneArgs(st=self._set("static"), dy=self._set("dynamic"), raw=True, use_deform=deform,
+                          motion_coeff=self.p("motion_coeff").view(self.nd, self.num_basis) if deform else None,
+                          time_ind=self.time_ind if deform else None, basis_t=basis_all[0] if deform else None,
+                          table=self.p("table") if deform else None, spatial_lr_scale=self.spatial_lr_scale,
+                          frame_order=self.frame_order, frame_offsets=self.frame_offsets)
+        sc_s = engine._scene_struct(scene)
+        gst, gdy = engine._setgrad_struct(self._setgrad("static")), engine._setgrad_struct(self._setgrad("dynamic"))
+        check(lib.rdg_sh_grad_views(C.byref(sc_s), self.sh_degree, v_total, ptr(viewmats_all), ptr(basis_all),
+                                    ptr(self.dcolor_all), 1.0 / v_total, C.byref(gst), C.byref(gdy), _lib.stream_ptr()))
+        self._mark("exchange")
 
     def total_loss(self) -> torch.Tensor:
         """photometric + w_p * pearson + alpha term (device scalar)."""

@@ -16,12 +16,12 @@ from oracle import deform_oracle as do
 from oracle import loss_oracle as lo
 from oracle import splat_oracle as so
 from rodygs_b200 import synthetic
-from rodygs_b200.trainer import PARAM_ORDER, allreduce_flat, flat_layout, shard_views
+from rodygs_b200.trainer import PARAM_ORDER, allgather_rows, allreduce_flat, flat_layout, sh_start, shard_views
 
 N, H, W, T, VIEWS = 600, 48, 64, 4, 4
 
 
-def _view_grads(sc, view, layout, total):
+def _view_grads(sc, view, layout, total, factors=False):
     cam = synthetic.make_camera(view, VIEWS, H, W, T)
     leaf = lambda t: t.detach().clone().requires_grad_(True)
     st = do.RawGaussians(**{k: leaf(v) for k, v in sc["static"].items()})
@@ -32,6 +32,7 @@ def _view_grads(sc, view, layout, total):
     out = so.rasterize(xyz, None, feat, None, op, scl, rot, cam.world_view_transform.t().contiguous(),
                        helpers.oracle_settings(cam, torch.zeros(3), 3))
     gt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(1000 + view))
+    out.pp.rgb.retain_grad()
     lo.photometric(out.color, gt).backward()
     flat = torch.zeros(total)
     def put(name, t):
@@ -42,6 +43,13 @@ def _view_grads(sc, view, layout, total):
         for k in PARAM_ORDER:
             put(f"{tag}.{k}", getattr(model, k))
     put("motion_coeff", coeff); put("table", table); put("basis_t", basis_t)
+    if factors:
+        # dL/d(rgb) after the SH clamp mask, zero for Gaussians this view does not see; the deformed means; campos
+        dcolor = torch.zeros(xyz.shape[0], 3)
+        dcolor[out.pp.idx] = out.pp.rgb.grad * (out.pp.rgb.detach() > 0)
+        V = cam.world_view_transform
+        campos = -(V[:3, :3].t() @ V[:3, 3])
+        return flat, dcolor, xyz.detach(), campos
     return flat
 
 
@@ -84,3 +92,66 @@ def test_view_sharded_allreduce_matches_sequential():
     ref /= VIEWS
     assert ref.abs().max() > 0
     assert torch.allclose(got, ref, rtol=1e-5, atol=1e-8)
+
+
+def _worker_factored(rank, world, port, ret):
+    """The exchange of SplatTrainStep.exchange_grads on CPU: all-gather the 12-byte factors of dL/dSH,
+    all-reduce only the non-SH range, rebuild dL/dSH of all views from the factors."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sc = synthetic.make_scene(N, H, W, T, seed=3)
+        ns, nd = sc["static"]["xyz"].shape[0], sc["dynamic"]["xyz"].shape[0]
+        layout, total = flat_layout(ns, nd, 16, T)
+        n_plain = sh_start(layout)
+        per_rank = VIEWS // world
+        flat = torch.zeros(total)
+        local = torch.zeros(per_rank, 3, ns + nd, 3)      # per view: factors, deformed means, (campos in row 0)
+        for slot in range(per_rank):
+            v = rank * per_rank + slot                      # rank-major view order, as exchange_grads expects
+            f, dcolor, xyz, campos = _view_grads(sc, v, layout, total, factors=True)
+            flat += f
+            local[slot, 0], local[slot, 1] = dcolor, xyz
+            local[slot, 2, 0] = campos
+        flat[n_plain:] = 0.0                                # the SH blocks are NOT exchanged
+        gathered = torch.zeros(VIEWS, 3, ns + nd, 3)
+        allgather_rows(local, gathered)
+        allreduce_flat(flat[:n_plain], 1.0 / VIEWS)
+        g = so.sh_grad_from_factors(3, [gathered[v, 1] for v in range(VIEWS)], [gathered[v, 2, 0] for v in range(VIEWS)],
+                                    [gathered[v, 0] for v in range(VIEWS)]) / VIEWS
+        for tag, lo_, hi_ in (("static", 0, ns), ("dynamic", ns, ns + nd)):
+            o, _ = layout[f"{tag}.features_dc"]
+            flat[o:o + (hi_ - lo_) * 3] = g[lo_:hi_, :1].reshape(-1)
+            o, _ = layout[f"{tag}.features_rest"]
+            flat[o:o + (hi_ - lo_) * 45] = g[lo_:hi_, 1:].reshape(-1)
+        if rank == 0:
+            ret.put(flat.clone())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_factored_sh_exchange_matches_sequential():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_worker_factored, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = ret.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sc = synthetic.make_scene(N, H, W, T, seed=3)
+    layout, total = flat_layout(sc["static"]["xyz"].shape[0], sc["dynamic"]["xyz"].shape[0], 16, T)
+    ref = torch.zeros(total)
+    for v in range(VIEWS):
+        ref += _view_grads(sc, v, layout, total)
+    ref /= VIEWS
+    o, _ = layout["static.features_rest"]
+    assert ref[o:].abs().max() > 0
+    assert helpers.rel_err(got, ref) < 1e-5
+    assert torch.allclose(got, ref, rtol=1e-3, atol=1e-7)

@@ -160,3 +160,47 @@ def test_fused_adam_matches_torch_adam():
         _lib.check(lib.rdg_adam(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 1.6e-4, 0.9, 0.999,
                                 1e-15, it, 1.0, _lib.stream_ptr()))
     assert torch.allclose(p, p_ref.detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_factored_sh_exchange_equals_direct_sum_over_views():
+    """The data-parallel exchange (12-byte factors of dL/dSH + rdg_sh_grad_views) gives the same mean gradient
+    over a step's views as summing the per-view gradients that the plain backward writes - here with one rank
+    holding all views, which exercises preprocess_bwd's factor output and the rebuild kernel end to end."""
+    N, H, W, T, VIEWS = 50_000, 192, 256, 6, 3
+    scene = synthetic.to_device(synthetic.make_scene(N, H, W, T, seed=4), "cuda")
+    step = SplatTrainStep(scene, H, W, sh_degree=3, w_pearson=0.05, w_alpha=0.01)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    views = []
+    for v in range(VIEWS):
+        cam = synthetic.make_camera(v, 8, H, W, T)
+        vm = cam.world_view_transform.t().contiguous().cuda()
+        pm = cam.projection_matrix.t().contiguous().cuda()
+        bt = step.p("table")[cam.time_index].clone()
+        gt = torch.rand(3, H, W, device="cuda", generator=gen)
+        gtd = torch.rand(1, H, W, device="cuda", generator=gen)
+        views.append((cam, vm, pm, bt, gt, gtd))
+    # reference: plain backward per view, summed
+    ref = torch.zeros_like(step.grads)
+    for cam, vm, pm, bt, gt, gtd in views:
+        step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, bt, gt, gtd)
+        ref += step.grads
+    ref /= VIEWS
+    # factored: per view the non-SH gradients accumulate, the SH blocks come from the factors
+    step.enable_factored_exchange(views_per_rank=VIEWS, world_size=1)
+    step.grads.zero_()
+    for slot, (cam, vm, pm, bt, gt, gtd) in enumerate(views):
+        step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, bt, gt, gtd, accumulate=slot > 0, dcolor_slot=slot)
+    step.exchange_grads(torch.stack([v[1] for v in views]).contiguous(), torch.stack([v[3] for v in views]).contiguous())
+    got = step.grads
+    from rodygs_b200.trainer import sh_start
+    n_plain = sh_start(step.layout)
+    o_tab, _ = step.layout["table"]
+    assert ref[n_plain:].abs().max().item() > 0
+    for name in ("static.features_dc", "static.features_rest", "dynamic.features_dc", "dynamic.features_rest",
+                 "static.xyz", "dynamic.xyz", "dynamic.rotation", "motion_coeff", "table"):
+        o, shp = step.layout[name]
+        n = 1
+        for s in shp:
+            n *= s
+        a, b = got[o:o + n], ref[o:o + n]
+        assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-12, name
