@@ -234,7 +234,7 @@ def run_ours(args, rank, world, local_rank):
     factored = world > 1 and not args.plain_allreduce and not args.forward_only
     all_vm, all_bt = [], []
     if factored:
-        step.enable_factored_exchange(views_per_rank=1, world_size=world)
+        step.enable_factored_exchange(views_per_rank=1, world_size=world, copy_engine_gather=not args.nccl_gather)
         for j in range(len(my_views)):
             cs = [synthetic.make_camera(r + j * world, n_views, H, W, T) for r in range(world)]
             all_vm.append(torch.stack([c.world_view_transform.t().contiguous() for c in cs]).to(dev).contiguous())
@@ -354,7 +354,7 @@ def run_ours(args, rank, world, local_rank):
     }
     total_bytes = synthetic.algorithmic_bytes(N, V, nd, D, P, K, forward_only=args.forward_only)
     peak, peak_src = load_peaks()
-    dom = max(stage_ms, key=stage_ms.get) if stage_ms else "blend_bwd"
+    dom = max((k for k in stage_ms if k in stage_bytes), key=stage_ms.get) if stage_ms else "blend_bwd"
     dom_ms = stage_ms.get(dom, float("nan"))
     achieved = stage_bytes[dom] / (dom_ms * 1e-3) / 1e9
     traffic = None
@@ -414,6 +414,8 @@ def main():
     ap.add_argument("--adam", action="store_true")
     ap.add_argument("--forward-only", action="store_true", help="BASELINE config 5: inference render sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true",
+                    help="N>1: gather the dL/dSH factors with NCCL instead of copy-engine pulls over symmetric memory (A/B)")
     ap.add_argument("--plain-allreduce", action="store_true",
                     help="N>1: all-reduce the whole flat gradient buffer instead of the factored SH exchange (A/B)")
     args = ap.parse_args()

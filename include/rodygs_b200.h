@@ -201,6 +201,10 @@ int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, const RdgGeom
  * with x(t_v) the (deformed, scene.raw) mean at view v's time.  viewmatrices [V,16] glm storage, basis_ts [V,K,7]
  * (B(t_v), needed when scene.use_deform), dcolor [V,N,3] as written by rdg_preprocess_bwd through
  * RdgSceneGrad.dcolor (gathered from all ranks).  Overwrites grad_*->sh_dc / sh_rest; V <= 16. */
+/* The same factors straight from the blend backward's accumulators (acc rows 6..8, clamp mask applied), so that
+ * their all-gather can start before rdg_preprocess_bwd runs.  dcolor [N,3]. */
+int rdg_dcolor_from_acc(int64_t n, const float* acc, const uint8_t* clamped, float* dcolor, void* stream);
+
 int rdg_sh_grad_views(const RdgScene* scene, int32_t sh_degree, int32_t n_views, const float* viewmatrices,
                       const float* basis_ts, const float* dcolor, float scale, const RdgSetGrad* grad_static,
                       const RdgSetGrad* grad_dynamic, void* stream);

@@ -85,6 +85,7 @@ SYMBOLS = {
                                 C.POINTER(RdgImage), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "rdg_preprocess_bwd": (C.c_int, [C.POINTER(RdgScene), C.POINTER(RdgView), C.POINTER(RdgGeom), c_ptr,
                                      C.POINTER(RdgSceneGrad), c_ptr]),
+    "rdg_dcolor_from_acc": (C.c_int, [C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "rdg_sh_grad_views": (C.c_int, [C.POINTER(RdgScene), C.c_int32, C.c_int32, c_ptr, c_ptr, c_ptr, C.c_float,
                                     C.POINTER(RdgSetGrad), C.POINTER(RdgSetGrad), c_ptr]),
     "rdg_l1_dssim_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),

@@ -11,6 +11,7 @@
 // HBM-bound: reads 12 B (xyz) + 12 B per view [+ 68 B coefficients / birth frame for a dynamic Gaussian],
 // writes 12*K B.  One thread per Gaussian, 256-Gaussian chunks of one model; the chunk's 46 KB of dSH
 // rows leave through shared memory by one TMA bulk store (coalesced, no LSU store instructions).
+#include <stdlib.h>
 #include "scene.cuh"
 #include "tma.cuh"
 
@@ -156,6 +157,33 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) sh_grad_views_kernel(const ShGra
     if (threadIdx.x == 0 && store_pending) rdg_bulk_store_wait_read();
 }
 
+// dcolor[i] = acc[i][6..8] with the channels the forward pass clamped at zero masked out: the factors of dL/dSH,
+// available as soon as the blend backward is done (so their all-gather overlaps the per-Gaussian backward)
+__global__ void __launch_bounds__(RDG_BLOCK) dcolor_from_acc_kernel(int64_t n, const float* __restrict__ acc,
+                                                                    const uint8_t* __restrict__ clamped, float* __restrict__ dcolor) {
+    for (int64_t i = (int64_t)blockIdx.x * RDG_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * RDG_BLOCK) {
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(acc + i * 12 + 4));   // dC, dop, dr, dg
+        const float gb = __ldg(acc + i * 12 + 8);
+        const bool any = g1.z != 0.f || g1.w != 0.f || gb != 0.f;
+        const unsigned cl = any ? clamped[i] : 0u;     // only written for visible Gaussians; the others have zero rows
+        float* o = dcolor + i * 3;
+        o[0] = (cl & 1u) ? 0.f : g1.z;
+        o[1] = (cl & 2u) ? 0.f : g1.w;
+        o[2] = (cl & 4u) ? 0.f : gb;
+    }
+}
+
+extern "C" int rdg_dcolor_from_acc(int64_t n, const float* acc, const uint8_t* clamped, float* dcolor, void* stream) {
+    RDG_CHECK_ARG(acc && clamped && dcolor, "null argument");
+    if (n <= 0) return RDG_OK;
+    const int64_t want = (n + RDG_BLOCK - 1) / RDG_BLOCK;
+    const int grid = (int)(want < (int64_t)RDG_SM_COUNT * 8 ? want : (int64_t)RDG_SM_COUNT * 8);
+    dcolor_from_acc_kernel<<<grid, RDG_BLOCK, 0, (cudaStream_t)stream>>>(n, acc, clamped, dcolor);
+    RDG_CHECK_LAUNCH();
+    rdg_count_launches(1);
+    return RDG_OK;
+}
+
 template <int DEG>
 static int launch_sgv(const ShGradParams& p, int grid, size_t smem, cudaStream_t s) {
     RDG_CUDA(cudaFuncSetAttribute(sh_grad_views_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -185,7 +213,10 @@ extern "C" int rdg_sh_grad_views(const RdgScene* scene, int32_t sh_degree, int32
     p.use_tma = ((((uintptr_t)grad_static->sh_rest | (uintptr_t)grad_dynamic->sh_rest) & 15u) == 0) ? 1 : 0;
     const size_t smem = (size_t)RDG_BLOCK * SH_ROW * sizeof(float);
     const int64_t chunks = (scene->n_static + RDG_BLOCK - 1) / RDG_BLOCK + (scene->n_dynamic + RDG_BLOCK - 1) / RDG_BLOCK;
-    const int64_t cap = (int64_t)RDG_SM_COUNT * 2;
+    // persistent grid, two CTAs per SM.  RDG_SGV_SMS (experiments): leave the other SMs to a collective that runs
+    // at the same time - these CTAs take the whole register file of the SMs they sit on.
+    static const int sms = [] { const char* e = getenv("RDG_SGV_SMS"); const int v = e ? atoi(e) : 0; return v > 0 && v <= RDG_SM_COUNT ? v : RDG_SM_COUNT; }();
+    const int64_t cap = (int64_t)sms * 2;
     const int grid = (int)(chunks < cap ? chunks : cap);
     cudaStream_t s = (cudaStream_t)stream;
     int rc;

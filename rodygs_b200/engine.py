@@ -355,8 +355,11 @@ def _setgrad_struct(g: SetGrads) -> RdgSetGrad:
     return out
 
 
-def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: SceneGrads, stage_hook=None):
-    """blend backward -> preprocess backward.  Writes into the tensors of `grads`."""
+def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: SceneGrads, stage_hook=None,
+                    after_blend=None):
+    """blend backward -> preprocess backward.  Writes into the tensors of `grads`.
+    after_blend: data-parallel mode - called as soon as grads.dcolor (the factors of dL/dSH) is final, i.e.
+    right after the blend backward, so that their all-gather overlaps the per-Gaussian backward."""
     lib = _lib.load()
     dev = state.view.viewmatrix.device
     stream = _lib.stream_ptr()
@@ -375,13 +378,17 @@ def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: Sce
     dL_dcolor, dL_ddepth, dL_dalpha = c(dL_dcolor), c(dL_ddepth), c(dL_dalpha)
     check(lib.rdg_blend_bwd(n, C.byref(gm_s), C.byref(bins), C.byref(vw_s), C.byref(img),
                             ptr(dL_dcolor), ptr(dL_ddepth), ptr(dL_dalpha), ptr(acc), stream))
+    early = after_blend is not None and grads.dcolor is not None and state.scene.colors_precomp is None
+    if early:
+        check(lib.rdg_dcolor_from_acc(n, ptr(acc), ptr(state.geom["clamped"]), ptr(grads.dcolor), stream))
+        after_blend()
     if stage_hook:
         stage_hook("blend_bwd")
     g = RdgSceneGrad()
     g.st, g.dy = _setgrad_struct(grads.st), _setgrad_struct(grads.dy)
     g.colors_precomp, g.means2D, g.viewmatrix = ptr(grads.colors_precomp), ptr(grads.means2D), ptr(grads.viewmatrix)
     g.motion_coeff, g.table, g.basis_t = ptr(grads.motion_coeff), ptr(grads.table), ptr(grads.basis_t)
-    g.dcolor = ptr(grads.dcolor)
+    g.dcolor = None if early else ptr(grads.dcolor)
     if state.scene.use_deform and state.scene.frame_order is not None and grads.table is not None:
         if grads.g7_scratch is None:
             grads.g7_scratch = torch.empty(state.scene.motion_coeff.shape[0], 8, dtype=torch.float32, device=dev)

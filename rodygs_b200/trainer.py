@@ -133,6 +133,7 @@ class SplatTrainStep:
         lib = _lib.load()
         self._ws_bytes = int(lib.rdg_l1_dssim_workspace_bytes(3, self.H, self.W))
         self._loss_ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.dev)
+        self.views_per_rank = 1
         self.last_state: Optional[engine.FwdState] = None
         self.stage_events = None   # set by enable_stage_timing()
 
@@ -235,8 +236,11 @@ class SplatTrainStep:
                                motion_coeff=self.g("motion_coeff").view(self.nd, self.num_basis) if deform else None,
                                table=self.g("table") if deform else None, basis_t=self.g("basis_t") if deform else None,
                                g7_scratch=self._g7)
+            hook = None
+            if dcolor_slot is not None and dcolor_slot == self.views_per_rank - 1:
+                hook = self._start_gather      # the factors of every local view are final: gather them now
             engine.render_backward(state, self.dL_dcolor, self.dL_ddepth if use_depth else None,
-                                   self.dL_dalpha if use_alpha else None, grads, stage_hook=self._mark)
+                                   self.dL_dalpha if use_alpha else None, grads, stage_hook=self._mark, after_blend=hook)
         finally:
             self.grads = saved
         if accumulate:
@@ -249,27 +253,99 @@ class SplatTrainStep:
         allreduce_flat(self.grads, scale, self.pg)
 
     # -- data-parallel exchange with factored SH gradients -----------------------------------------
-    def enable_factored_exchange(self, views_per_rank: int, world_size: int):
-        """Buffers for exchange_grads(): the local factors [views_per_rank, N, 3] and the gathered ones."""
+    def enable_factored_exchange(self, views_per_rank: int, world_size: int, copy_engine_gather: bool = True,
+                                 gather_streams: int = 4):
+        """Buffers and the side streams for exchange_grads(): the local factors [views_per_rank, N, 3], the gathered
+        ones, and a communication stream on which the collectives overlap the backward kernels.
+
+        copy_engine_gather: keep the GATHERED factors in symmetric memory (torch.distributed._symmetric_memory) and
+        let every rank push its own block into all peers' buffers with plain device-to-device copies - NVLink
+        through the copy engines, no SMs, so the gather really runs under the per-Gaussian backward (whose
+        persistent CTAs own the whole register file; an NCCL kernel only gets in once they retire).  Falls back to
+        NCCL's all-gather when symmetric memory cannot be set up."""
+        import torch.distributed as dist
         n = self.ns + self.nd
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.views_per_rank, self.world_size = int(views_per_rank), int(world_size)
+        v_total = self.views_per_rank * self.world_size
+        self._symm = None
+        self.dcolor_all = None
+        if copy_engine_gather and self.world_size > 1 and dist.is_initialized():
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                buf = symm_mem.empty(v_total, n, 3, dtype=torch.float32, device=self.dev)
+                group = self.pg if self.pg is not None else dist.group.WORLD
+                self._symm = symm_mem.rendezvous(buf, group)
+                self.dcolor_all = buf
+                self._rank = dist.get_rank(group)
+                k = self.views_per_rank
+                # my block inside every peer's gathered buffer
+                self._peer_blocks = [self._symm.get_buffer(r, buf.shape, torch.float32)[self._rank * k:(self._rank + 1) * k]
+                                     for r in range(self.world_size)]
+                self._gather_streams = [torch.cuda.Stream(device=self.dev) for _ in range(max(1, int(gather_streams)))]
+                self._ev_push = [torch.cuda.Event() for _ in self._gather_streams]
+            except Exception as e:   # noqa: BLE001 - any failure here only costs the overlap, never correctness
+                print(f"rodygs_b200: symmetric-memory gather unavailable ({type(e).__name__}: {e}); using NCCL all-gather")
+                self._symm = None
+                self.dcolor_all = None
+        if self.dcolor_all is None:
+            self.dcolor_all = torch.zeros(v_total, n, 3, **f32)
+        self.dcolor_all.zero_()
         self.dcolor_local = torch.zeros(self.views_per_rank, n, 3, **f32)
-        self.dcolor_all = torch.zeros(self.views_per_rank * self.world_size, n, 3, **f32)
+        self.comm_stream = torch.cuda.Stream(device=self.dev)
+        self._ev_factors, self._ev_gathered = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_backward, self._ev_reduced = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_barrier = torch.cuda.Event()
+        self._gather_started = False
+
+    def _start_gather(self):
+        """All-gather of the factors on the communication stream (called right after the blend backward)."""
+        self._ev_factors.record()
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(self._ev_factors)
+            if self._symm is not None:
+                # every rank is done reading the previous step's gathered factors (its rebuild kernel precedes
+                # _ev_factors on its compute stream), then the pushes go out on a few streams at once
+                self._symm.barrier()
+                self._ev_barrier.record(self.comm_stream)
+                ns = len(self._gather_streams)
+                for i, st in enumerate(self._gather_streams):
+                    st.wait_event(self._ev_barrier)
+                    with torch.cuda.stream(st):
+                        for s in range(i, self.world_size, ns):
+                            r = (self._rank + s) % self.world_size
+                            self._peer_blocks[r].copy_(self.dcolor_local, non_blocking=True)
+                        self._ev_push[i].record(st)
+                for ev in self._ev_push:
+                    self.comm_stream.wait_event(ev)
+                self._symm.barrier()                    # every rank's pushes have landed everywhere
+            else:
+                allgather_rows(self.dcolor_local, self.dcolor_all, self.pg)
+            self._ev_gathered.record(self.comm_stream)
+        self._gather_started = True
 
     def exchange_grads(self, viewmats_all: torch.Tensor, basis_all: torch.Tensor):
         """Finish a data-parallel step whose local views ran with dcolor_slot=0..views_per_rank-1:
-        all-gather the 12-byte factors of dL/dSH (81 % of the gradient message as 192-byte blocks),
-        all-reduce everything else, rebuild dL/dSH of ALL views from the factors (rdg_sh_grad_views).
+        all-gather the 12-byte factors of dL/dSH (81 % of the gradient message as 192-byte blocks; started right
+        after the blend backward, so it overlaps the per-Gaussian backward), all-reduce everything else on the
+        communication stream while this stream rebuilds dL/dSH of ALL views from the factors (rdg_sh_grad_views).
         viewmats_all [V,4,4] glm storage and basis_all [V,K,7] in rank-major view order (rank r holds views
         r*views_per_rank ..); the result in self.grads is the mean over the V views."""
         lib = _lib.load()
         v_total = self.views_per_rank * self.world_size
         n_plain = sh_start(self.layout)
-        allgather_rows(self.dcolor_local, self.dcolor_all, self.pg)
-        allreduce_flat(self.grads[:n_plain], 1.0 / self.world_size, self.pg)
-        if self.views_per_rank > 1:
-            self.grads[:n_plain].mul_(1.0 / self.views_per_rank)
+        cur = torch.cuda.current_stream()
+        if not self._gather_started:
+            self._start_gather()
+        self._gather_started = False
+        self._ev_backward.record()
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(self._ev_backward)
+            allreduce_flat(self.grads[:n_plain], 1.0 / self.world_size, self.pg)
+            if self.views_per_rank > 1:
+                self.grads[:n_plain].mul_(1.0 / self.views_per_rank)
+            self._ev_reduced.record(self.comm_stream)
+        cur.wait_event(self._ev_gathered)
         deform = self.nd > 0
         scene = SceneArgs(st=self._set("static"), dy=self._set("dynamic"), raw=True, use_deform=deform,
                           motion_coeff=self.p("motion_coeff").view(self.nd, self.num_basis) if deform else None,
@@ -280,6 +356,7 @@ class SplatTrainStep:
         gst, gdy = engine._setgrad_struct(self._setgrad("static")), engine._setgrad_struct(self._setgrad("dynamic"))
         check(lib.rdg_sh_grad_views(C.byref(sc_s), self.sh_degree, v_total, ptr(viewmats_all), ptr(basis_all),
                                     ptr(self.dcolor_all), 1.0 / v_total, C.byref(gst), C.byref(gdy), _lib.stream_ptr()))
+        cur.wait_event(self._ev_reduced)
         self._mark("exchange")
 
     def total_loss(self) -> torch.Tensor:
