@@ -77,6 +77,9 @@ __device__ __forceinline__ float4 rdg_lds128(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void rdg_sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void rdg_sts32_if(bool on, uint32_t addr, float v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.f32 [%0], %1;\n\t}" ::"r"(addr), "f"(v), "r"((uint32_t)on) : "memory");
+}
 __device__ __forceinline__ void rdg_cp16(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -85,6 +88,25 @@ __device__ __forceinline__ void rdg_cp8(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void rdg_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void rdg_cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Packed FP32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for the same operation on the two
+// pixels of a lane; a scalar operand is broadcast for free).  Individually rounded IEEE operations, so
+// the packed and the scalar inner loops produce the same alpha bit for bit.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t rdg_pk(float lo, float hi) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2_t rdg_bc(float x) { return rdg_pk(x, x); }
+__device__ __forceinline__ void rdg_unpk(f2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2_t rdg_fma2(f2_t a, f2_t b, f2_t c) { f2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2_t rdg_mul2(f2_t a, f2_t b) { f2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2_t rdg_add2(f2_t a, f2_t b) { f2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// power of the two pixels of a lane (same column, rows y0 and y0 + 1); npixy = (-y0, -y1).  Same operation
+// order and roundings as rdg_alpha.
+__device__ __forceinline__ f2_t rdg_power2(float Adx2, float Bdx, float C, float py, f2_t npixy, f2_t& dy) {
+    dy = rdg_add2(rdg_bc(py), npixy);
+    const f2_t q = rdg_fma2(rdg_mul2(rdg_bc(C), dy), dy, rdg_bc(Adx2));
+    return rdg_fma2(rdg_bc(-0.5f), q, rdg_mul2(rdg_bc(-Bdx), dy));
+}
 
 // alpha = min(0.99, o * exp(power)), power = -(A dx^2 + C dy^2)/2 - B dx dy.  Identical
 // instruction sequence in both passes so that the skip decisions replayed by the backward
@@ -190,6 +212,7 @@ __device__ __forceinline__ void rdg_init_null(Staged& sm) {
     }
 }
 
+template <bool PK>
 __global__ void __launch_bounds__(BATCH, 6) blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
                                                              const float4* __restrict__ p0, const float4* __restrict__ p1,
                                                              const float2* __restrict__ p2, const float* __restrict__ bg,
@@ -265,6 +288,54 @@ __global__ void __launch_bounds__(BATCH, 6) blend_fwd_kernel(const uint2* __rest
         const int nmax = rdg_compact4<false>(sm, sm.mask[buf], cnt, warp, lane, live);
         const uint32_t boff = (uint32_t)(buf * NSLOT) * 16u;
         uint32_t j_next = rdg_lds16(my_list);
+        if constexpr (PK) {
+            const f2_t npixy = rdg_pk(-pixy0, -pixy1);
+            f2_t T2 = rdg_pk(T0, T1), r2 = rdg_pk(r0, r1), g2 = rdg_pk(g0, g1), b2 = rdg_pk(b0, b1), d2 = rdg_pk(d0, d1);
+            for (int i = 0; i < nmax; ++i) {
+                const uint32_t j = j_next;
+                j_next = rdg_lds16(my_list + 2u * (i + 1));
+                const uint32_t o16 = boff + (j << 4);
+                const float4 a = rdg_lds128(sa + o16);
+                const float4 b = rdg_lds128(sb + o16);
+                const float2 c = rdg_lds64(sc + (o16 >> 1));
+                const float dx = a.x - pixx;
+                const float Adx2 = (a.z * dx) * dx, Bdx = a.w * dx;
+                const uint32_t here = (uint32_t)base + j + 1u;
+                f2_t dy;
+                const f2_t power = rdg_power2(Adx2, Bdx, b.x, a.y, npixy, dy);
+                float pw0, pw1, e0, e1;
+                rdg_unpk(power, pw0, pw1);
+                rdg_unpk(rdg_mul2(power, rdg_bc(1.4426950408889634f)), e0, e1);
+                float oG0, oG1;
+                rdg_unpk(rdg_mul2(rdg_bc(b.y), rdg_pk(rdg_ex2(e0), rdg_ex2(e1))), oG0, oG1);
+                const float al0 = fminf(RDG_ALPHA_MAX, oG0), al1 = fminf(RDG_ALPHA_MAX, oG1);
+                const bool on0 = (pw0 <= 0.0f) && (al0 >= RDG_ALPHA_MIN) && !done0;
+                const bool on1 = (pw1 <= 0.0f) && (al1 >= RDG_ALPHA_MIN) && !done1;
+                const f2_t al2 = rdg_pk(al0, al1);
+                const f2_t test2 = rdg_mul2(T2, rdg_fma2(al2, rdg_bc(-1.0f), rdg_bc(1.0f)));
+                float tt0, tt1, w0, w1, Tc0, Tc1;
+                rdg_unpk(test2, tt0, tt1);
+                rdg_unpk(rdg_mul2(al2, T2), w0, w1);
+                rdg_unpk(T2, Tc0, Tc1);
+                const bool stop0 = on0 && (tt0 < RDG_T_STOP), stop1 = on1 && (tt1 < RDG_T_STOP);
+                const bool upd0 = on0 && !stop0, upd1 = on1 && !stop1;
+                done0 = done0 || stop0;
+                done1 = done1 || stop1;
+                const f2_t wgt2 = rdg_pk(upd0 ? w0 : 0.0f, upd1 ? w1 : 0.0f);
+                r2 = rdg_fma2(rdg_bc(b.z), wgt2, r2);
+                g2 = rdg_fma2(rdg_bc(b.w), wgt2, g2);
+                b2 = rdg_fma2(rdg_bc(c.x), wgt2, b2);
+                d2 = rdg_fma2(rdg_bc(c.y), wgt2, d2);
+                T2 = rdg_pk(upd0 ? tt0 : Tc0, upd1 ? tt1 : Tc1);
+                last0 = upd0 ? here : last0;
+                last1 = upd1 ? here : last1;
+            }
+            rdg_unpk(T2, T0, T1);
+            rdg_unpk(r2, r0, r1);
+            rdg_unpk(g2, g0, g1);
+            rdg_unpk(b2, b0, b1);
+            rdg_unpk(d2, d0, d1);
+        } else {
         for (int i = 0; i < nmax; ++i) {
             const uint32_t j = j_next;
             j_next = rdg_lds16(my_list + 2u * (i + 1));            // one entry ahead (rows are padded): off the critical path
@@ -305,6 +376,7 @@ __global__ void __launch_bounds__(BATCH, 6) blend_fwd_kernel(const uint2* __rest
                 last1 = upd ? here : last1;
             }
         }
+        }
     }
     rdg_cp_wait_all();
     const size_t hw = (size_t)H * W;
@@ -337,18 +409,36 @@ __global__ void __launch_bounds__(BATCH, 6) blend_fwd_kernel(const uint2* __rest
 // Reduce-scatter of ten per-lane values over a quarter-warp (8 lanes) in 10 shuffles.
 // On return lane l holds the quarter total of v[5*b2 + b1 + 2*b0] in `r_main` (b2 b1 b0 = bits
 // of l & 7) and the lanes with (l & 3) == 0 hold the total of v[5*b2 + 4] in `r_extra`.
+template <bool PK = false>
 __device__ __forceinline__ void rdg_reduce_q10(const float (&v)[10], int lane, float& r_main, float& r_extra) {
     const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
     float a[5];
+    if constexpr (PK) {
+        float k[5], t[5];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const float keep = b2 ? v[i + 5] : v[i], send = b2 ? v[i] : v[i + 5];
-        a[i] = keep + __shfl_xor_sync(FULL, send, 4);
+        for (int i = 0; i < 5; ++i) {
+            k[i] = b2 ? v[i + 5] : v[i];
+            t[i] = __shfl_xor_sync(FULL, b2 ? v[i] : v[i + 5], 4);
+        }
+        rdg_unpk(rdg_add2(rdg_pk(k[0], k[1]), rdg_pk(t[0], t[1])), a[0], a[1]);
+        rdg_unpk(rdg_add2(rdg_pk(k[2], k[3]), rdg_pk(t[2], t[3])), a[2], a[3]);
+        a[4] = k[4] + t[4];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const float keep = b2 ? v[i + 5] : v[i], send = b2 ? v[i] : v[i + 5];
+            a[i] = keep + __shfl_xor_sync(FULL, send, 4);
+        }
     }
     const float k0 = b1 ? a[1] : a[0], s0 = b1 ? a[0] : a[1];
     const float k1 = b1 ? a[3] : a[2], s1 = b1 ? a[2] : a[3];
-    const float q0 = k0 + __shfl_xor_sync(FULL, s0, 2);
-    const float q1 = k1 + __shfl_xor_sync(FULL, s1, 2);
+    float q0, q1;
+    if constexpr (PK) {
+        rdg_unpk(rdg_add2(rdg_pk(k0, k1), rdg_pk(__shfl_xor_sync(FULL, s0, 2), __shfl_xor_sync(FULL, s1, 2))), q0, q1);
+    } else {
+        q0 = k0 + __shfl_xor_sync(FULL, s0, 2);
+        q1 = k1 + __shfl_xor_sync(FULL, s1, 2);
+    }
     const float q2 = a[4] + __shfl_xor_sync(FULL, a[4], 2);
     const float k = b0 ? q1 : q0, s = b0 ? q0 : q1;
     r_main = k + __shfl_xor_sync(FULL, s, 1);
@@ -364,6 +454,7 @@ __device__ __forceinline__ void rdg_bwd_issue(uint32_t sa, uint32_t sb, uint32_t
     rdg_cp8(sc + (o16 >> 1), p2 + id);
 }
 
+template <bool PK>
 __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
                                                              const float4* __restrict__ p0, const float4* __restrict__ p1,
                                                              const float2* __restrict__ p2, const float* __restrict__ bg,
@@ -431,7 +522,6 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
     const uint32_t sa = rdg_saddr(&sm.a[0][0]), sb = rdg_saddr(&sm.b[0][0]), sc = rdg_saddr(&sm.c[0][0]);
     const uint32_t my_list = rdg_saddr(&sm.list[sub][0]);
     const uint32_t pool_main = rdg_saddr(pool) + 4u * (uint32_t)(5 * ((lane >> 2) & 1) + ((lane >> 1) & 1) + 2 * (lane & 1));
-    const uint32_t pool_extra = rdg_saddr(pool) + 4u * (uint32_t)(5 * ((lane >> 2) & 1) + 4);
     const bool own_extra = (lane & 3) == 0;
     const uint32_t sebase = rdg_saddr(&sm.ebase[0]);
 
@@ -492,6 +582,79 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
         const int nmax = rdg_compact4<true>(sm, sm.mask[buf], cnt2, warp, lane, 0xfu);
         const uint32_t boff = (uint32_t)(buf * NSLOT) * 16u;
         uint32_t ent_next = rdg_lds16(my_list);
+        if constexpr (PK) {
+            const f2_t npixy = rdg_pk(-pixy0, -pixy1);
+            const f2_t gr2 = rdg_pk(gr0, gr1), gg2 = rdg_pk(gg0, gg1), gb2 = rdg_pk(gb0, gb1), gd2 = rdg_pk(gd0, gd1),
+                       ga2 = rdg_pk(ga0, ga1);
+            f2_t T2 = rdg_pk(T0, T1), A2 = rdg_pk(A0, A1);
+            for (int i = 0; i < nmax; ++i) {
+                const uint32_t ent = ent_next;
+                ent_next = rdg_lds16(my_list + 2u * (i + 1));
+                const uint32_t j = ent & 0xffu;
+                const uint32_t o16 = boff + (j << 4);
+                const float4 a = rdg_lds128(sa + o16);
+                const float4 b = rdg_lds128(sb + o16);
+                const float2 c = rdg_lds64(sc + (o16 >> 1));
+                const uint32_t rec = (rdg_lds16(sebase + 2u * j) + (ent >> 8)) * (uint32_t)(PREC * 4);
+                const uint32_t pos = (uint32_t)pos0 - j;
+                const float dx = a.x - pixx;
+                const float Adx2 = (a.z * dx) * dx, Bdx = a.w * dx;
+                f2_t dy2;
+                const f2_t power = rdg_power2(Adx2, Bdx, b.x, a.y, npixy, dy2);
+                float pw0, pw1, e0, e1;
+                rdg_unpk(power, pw0, pw1);
+                rdg_unpk(rdg_mul2(power, rdg_bc(1.4426950408889634f)), e0, e1);
+                float G0 = rdg_ex2(e0), G1 = rdg_ex2(e1);
+                float oG0, oG1;
+                rdg_unpk(rdg_mul2(rdg_bc(b.y), rdg_pk(G0, G1)), oG0, oG1);
+                float al0 = fminf(RDG_ALPHA_MAX, oG0), al1 = fminf(RDG_ALPHA_MAX, oG1);
+                const bool on0 = (pw0 <= 0.0f) && (al0 >= RDG_ALPHA_MIN) && (pos < last0);
+                const bool on1 = (pw1 <= 0.0f) && (al1 >= RDG_ALPHA_MIN) && (pos < last1);
+                G0 = on0 ? G0 : 0.0f;
+                G1 = on1 ? G1 : 0.0f;
+                al0 = on0 ? al0 : 0.0f;
+                al1 = on1 ? al1 : 0.0f;
+                const f2_t al2 = rdg_pk(al0, al1);
+                float om0, om1;
+                rdg_unpk(rdg_fma2(al2, rdg_bc(-1.0f), rdg_bc(1.0f)), om0, om1);
+                const float inv0 = on0 ? rdg_rcp(om0) : 1.0f, inv1 = on1 ? rdg_rcp(om1) : 1.0f;
+                const f2_t inv2 = rdg_pk(inv0, inv1);
+                T2 = rdg_mul2(T2, inv2);                            // transmittance in front of this Gaussian
+                const f2_t wgt2 = rdg_mul2(al2, T2);
+                const f2_t P2 = rdg_fma2(rdg_bc(b.z), gr2, rdg_fma2(rdg_bc(b.w), gg2, rdg_fma2(rdg_bc(c.x), gb2, rdg_fma2(rdg_bc(c.y), gd2, ga2))));
+                const f2_t nIA = rdg_mul2(inv2, A2);
+                float nia0, nia1;
+                rdg_unpk(nIA, nia0, nia1);
+                const f2_t dLda2 = rdg_fma2(T2, P2, rdg_pk(-nia0, -nia1));
+                A2 = rdg_fma2(P2, wgt2, A2);
+                const f2_t t52 = rdg_mul2(rdg_pk(G0, G1), dLda2);   // d/dopacity
+                const f2_t w2 = rdg_mul2(rdg_bc(b.y), t52);         // dL/dG * G
+                const f2_t wx2 = rdg_mul2(w2, rdg_bc(dx)), wy2 = rdg_mul2(w2, dy2);
+                float wxa, wxb, wya, wyb, dya, dyb, t5a, t5b, wga, wgb;
+                rdg_unpk(wx2, wxa, wxb);
+                rdg_unpk(wy2, wya, wyb);
+                rdg_unpk(dy2, dya, dyb);
+                rdg_unpk(t52, t5a, t5b);
+                rdg_unpk(wgt2, wga, wgb);
+                float v[10];
+                v[0] = wxa + wxb;
+                v[1] = wya + wyb;
+                v[2] = v[0] * dx;
+                v[3] = fmaf(wxb, dyb, wxa * dya);
+                v[4] = fmaf(wyb, dyb, wya * dya);
+                v[5] = t5a + t5b;
+                v[6] = fmaf(wgb, gr1, wga * gr0);
+                v[7] = fmaf(wgb, gg1, wga * gg0);
+                v[8] = fmaf(wgb, gb1, wga * gb0);
+                v[9] = fmaf(wgb, gd1, wga * gd0);
+                float r_main, r_extra;
+                rdg_reduce_q10<true>(v, lane, r_main, r_extra);
+                rdg_sts32(pool_main + rec, r_main);
+                rdg_sts32_if(own_extra, pool_main + rec + 16u, r_extra);   // owner lanes (l & 3) == 0: main slot 5*b2, extra slot 5*b2 + 4
+            }
+            rdg_unpk(T2, T0, T1);
+            rdg_unpk(A2, A0, A1);
+        } else {
         for (int i = 0; i < nmax; ++i) {
             const uint32_t ent = ent_next;
             ent_next = rdg_lds16(my_list + 2u * (i + 1));          // one entry ahead (rows are padded): off the critical path
@@ -549,7 +712,8 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
             float r_main, r_extra;
             rdg_reduce_q10(v, lane, r_main, r_extra);
             rdg_sts32(pool_main + rec, r_main);
-            if (own_extra) rdg_sts32(pool_extra + rec, r_extra);
+            rdg_sts32_if(own_extra, pool_main + rec + 16u, r_extra);
+        }
         }
         __syncthreads();
         if (tid < cnt2) {
@@ -590,6 +754,12 @@ static bool rdg_use_v1() {
     return v;
 }
 
+// RDG_BLEND_PACKED=0 selects the scalar-FP32 inner loops (A/B switch; both produce the same alpha bits)
+static bool rdg_use_packed() {
+    static const bool v = [] { const char* e = getenv("RDG_BLEND_PACKED"); return !(e && e[0] == '0'); }();
+    return v;
+}
+
 extern "C" int rdg_blend_fwd(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view,
                              const RdgImage* out, void* stream) {
     if (rdg_use_v1()) return rdg_blend_fwd_v1(n, geom, bins, view, out, stream);
@@ -598,7 +768,8 @@ extern "C" int rdg_blend_fwd(int64_t n, const RdgGeom* geom, const RdgBins* bins
     RDG_CHECK_ARG(view->bg, "null background");
     const int W = view->width, H = view->height;
     const int gx = (W + RDG_TILE - 1) / RDG_TILE, gy = (H + RDG_TILE - 1) / RDG_TILE;
-    blend_fwd_kernel<<<gx * gy, BATCH, 0, (cudaStream_t)stream>>>(
+    auto kern = rdg_use_packed() ? blend_fwd_kernel<true> : blend_fwd_kernel<false>;
+    kern<<<gx * gy, BATCH, 0, (cudaStream_t)stream>>>(
         (const uint2*)bins->ranges, bins->vals_sorted, (const float4*)geom->p0, (const float4*)geom->p1,
         (const float2*)geom->p2, view->bg, W, H, gx, out->color, out->depth, out->alpha, out->final_T, out->n_contrib,
         bins->sub_masks);
@@ -615,7 +786,8 @@ extern "C" int rdg_blend_bwd(int64_t n, const RdgGeom* geom, const RdgBins* bins
     RDG_CHECK_ARG(fwd->final_T && fwd->n_contrib, "null forward state");
     const int W = view->width, H = view->height;
     const int gx = (W + RDG_TILE - 1) / RDG_TILE, gy = (H + RDG_TILE - 1) / RDG_TILE;
-    blend_bwd_kernel<<<gx * gy, BATCH, 0, (cudaStream_t)stream>>>(
+    auto kern = rdg_use_packed() ? blend_bwd_kernel<true> : blend_bwd_kernel<false>;
+    kern<<<gx * gy, BATCH, 0, (cudaStream_t)stream>>>(
         (const uint2*)bins->ranges, bins->vals_sorted, (const float4*)geom->p0, (const float4*)geom->p1,
         (const float2*)geom->p2, view->bg, W, H, gx, fwd->final_T, fwd->n_contrib, dL_dcolor, dL_ddepth, dL_dalpha, acc,
         bins->sub_masks);
