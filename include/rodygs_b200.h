@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RDG_ABI_VERSION 3
+#define RDG_ABI_VERSION 4
 #define RDG_TILE 16
 #define RDG_NUM_BASIS_MAX 16
 
@@ -261,6 +261,53 @@ int rdg_alpha_reg(const float* alpha, int64_t n, float weight, float* out_loss, 
  * torch.optim.Adam, eps 1e-15, one lr per group). step >= 1. */
 int rdg_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
              float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+
+/* ---- densification (next row) ---------------------------------- */
+
+/* Per-iteration statistics of the model being trained (src/trainer/rodygs.py:316-341,
+ * src/trainer/rodygs_static.py:317-319): for every row with radii > 0,
+ * max_radii2D = max(max_radii2D, radii), grad_accum += |means2D_grad[:, :2]|, denom += 1.
+ * radii / means2D_grad point at the first row of that model inside the concatenated scene. */
+int rdg_densify_stats(int64_t n, const int32_t* radii, const float* means2D_grad, float* max_radii2D,
+                      float* grad_accum, float* denom, void* stream);
+
+/* densify_and_prune (src/trainer/rodygs_static.py:285-301 with :170-283,303-315;
+ * src/trainer/rodygs_dynamic.py:150-197) as one stream compaction.
+ * rdg_densify_plan evaluates clone / split / prune on the n rows of one model and writes
+ *   counts[4] (device) = {A survivors, B clones, C kept split parents, S split-selected};
+ *   the new model has A + B + 2 C rows in the reference's final order [A | B | children copy 0 | copy 1];
+ *   map[3 n]  : entry j of the first A + B + 2 C = source row | kind << 30, kind 0 survivor, 1 clone, 2 / 3 split child;
+ *   split_rank[n] : rank of a split-selected row among the S (else -1) - child copy c of that row takes the
+ *                   noise row c * S + rank, the row layout of the reference's torch.normal call (:182-184).
+ * use_screen_size: the reference's `max_screen_size` is not None (iteration > opacity_reset_interval). */
+int64_t rdg_densify_workspace_bytes(int64_t n);
+int rdg_densify_plan(int64_t n, const float* scaling, int32_t scaling_width, const float* opacity,
+                     const float* grad_accum, const float* denom, float grad_threshold, float percent_dense,
+                     float extent, float min_opacity, int32_t use_screen_size, uint32_t* map,
+                     int32_t* split_rank, int32_t* counts, void* workspace, int64_t workspace_bytes, void* stream);
+
+enum RdgDensifyMode {
+    RDG_DENSIFY_COPY = 0,     /* dst[j] = src[map[j]]                                   (parameters, time, time index) */
+    RDG_DENSIFY_MOMENT = 1,   /* survivors keep the row, new rows get 0                  (Adam exp_avg / exp_avg_sq, utils.py:34-95) */
+    RDG_DENSIFY_XYZ = 2,      /* split children: R(q) (noise * exp(scaling)) + xyz      (rodygs_static.py:182-195) */
+    RDG_DENSIFY_SCALING = 3   /* split children: log(exp(scaling) / (0.8 * 2))           (:187-189) */
+};
+typedef struct RdgDensifyField {
+    const void* src;          /* [n, width] 32-bit elements */
+    void* dst;                /* [n_new, width] */
+    int32_t width;
+    int32_t mode;             /* RdgDensifyMode */
+} RdgDensifyField;
+
+/* Moves every field of the n_new = A + B + 2 C new rows in one pass (a warp per row).
+ * noise [2 S, 3]: unit normal samples; xyz / scaling / rotation: the ORIGINAL tensors (inputs of the split formula). */
+int rdg_densify_apply(int64_t n_new, const uint32_t* map, const int32_t* split_rank, const int32_t* counts,
+                      const float* noise, const RdgDensifyField* fields, int32_t n_fields, const float* xyz,
+                      const float* scaling, int32_t scaling_width, const float* rotation, void* stream);
+
+/* reset_opacity (src/trainer/rodygs_static.py:150-159): opacity = inverse_sigmoid(min(sigmoid(opacity), cap)),
+ * Adam moments of the group zeroed (src/trainer/utils.py:15-32; may be NULL). */
+int rdg_reset_opacity(int64_t n, float* opacity, float cap, float* exp_avg, float* exp_avg_sq, void* stream);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,10 @@ class RdgSceneGrad(C.Structure):
                 ("dcolor", c_ptr)]
 
 
+class RdgDensifyField(C.Structure):
+    _fields_ = [("src", c_ptr), ("dst", c_ptr), ("width", C.c_int32), ("mode", C.c_int32)]
+
+
 class RdgLossTerms(C.Structure):
     _fields_ = [("depth", c_ptr), ("gt_depth", c_ptr), ("w_pearson", C.c_float), ("pearson_eps", C.c_float),
                 ("dL_ddepth", c_ptr), ("alpha", c_ptr), ("w_alpha", C.c_float), ("dL_dalpha", c_ptr)]
@@ -97,6 +101,13 @@ SYMBOLS = {
                               c_ptr, c_ptr]),
     "rdg_adam": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                            C.c_int32, C.c_float, c_ptr]),
+    "rdg_densify_stats": (C.c_int, [C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "rdg_densify_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "rdg_densify_plan": (C.c_int, [C.c_int64, c_ptr, C.c_int32, c_ptr, c_ptr, c_ptr, C.c_float, C.c_float, C.c_float,
+                                   C.c_float, C.c_int32, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr]),
+    "rdg_densify_apply": (C.c_int, [C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, C.POINTER(RdgDensifyField), C.c_int32, c_ptr,
+                                    c_ptr, C.c_int32, c_ptr, c_ptr]),
+    "rdg_reset_opacity": (C.c_int, [C.c_int64, c_ptr, C.c_float, c_ptr, c_ptr, c_ptr]),
 }
 
 _lib = None
@@ -116,7 +127,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.rdg_abi_version() != 3:
+    if lib.rdg_abi_version() != 4:
         raise RuntimeError("librodygs_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -34,6 +34,7 @@ SOURCES = {
     "preprocess_bwd.cu": [],
     "sh_grad_views.cu": [],
     "loss.cu": [],
+    "densify.cu": [],
 }
 HEADERS = ["common.cuh", "scene.cuh", os.path.join("..", "..", "include", "rodygs_b200.h")]
 
