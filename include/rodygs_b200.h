@@ -262,6 +262,19 @@ int rdg_alpha_reg(const float* alpha, int64_t n, float weight, float* out_loss, 
 int rdg_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
              float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
 
+/* All parameter groups of one optimiser in ONE launch over the flat buffers (same arithmetic as rdg_adam):
+ * groups[k] = float range [begin, end) of param / grad / exp_avg / exp_avg_sq with its own learning rate
+ * (xyz, f_dc, f_rest = feature_lr / 20, opacity, scaling, rotation: rodygs_static.py:106-141; motion_coeff:
+ * rodygs_dynamic.py:92-123).  begin must be a multiple of 4 floats; n_groups <= 16. */
+typedef struct RdgAdamGroup {
+    int64_t begin;
+    int64_t end;
+    float lr;
+    int32_t reserved;
+} RdgAdamGroup;
+int rdg_adam_groups(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const RdgAdamGroup* groups,
+                    int32_t n_groups, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+
 /* ---- densification (next row) ---------------------------------- */
 
 /* Per-iteration statistics of the model being trained (src/trainer/rodygs.py:316-341,

@@ -65,6 +65,10 @@ class RdgDensifyField(C.Structure):
     _fields_ = [("src", c_ptr), ("dst", c_ptr), ("width", C.c_int32), ("mode", C.c_int32)]
 
 
+class RdgAdamGroup(C.Structure):
+    _fields_ = [("begin", C.c_int64), ("end", C.c_int64), ("lr", C.c_float), ("reserved", C.c_int32)]
+
+
 class RdgLossTerms(C.Structure):
     _fields_ = [("depth", c_ptr), ("gt_depth", c_ptr), ("w_pearson", C.c_float), ("pearson_eps", C.c_float),
                 ("dL_ddepth", c_ptr), ("alpha", c_ptr), ("w_alpha", C.c_float), ("dL_dalpha", c_ptr)]
@@ -101,6 +105,8 @@ SYMBOLS = {
                               c_ptr, c_ptr]),
     "rdg_adam": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                            C.c_int32, C.c_float, c_ptr]),
+    "rdg_adam_groups": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.POINTER(RdgAdamGroup), C.c_int32, C.c_float, C.c_float,
+                                  C.c_float, C.c_int32, C.c_float, c_ptr]),
     "rdg_densify_stats": (C.c_int, [C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "rdg_densify_workspace_bytes": (C.c_int64, [C.c_int64]),
     "rdg_densify_plan": (C.c_int, [C.c_int64, c_ptr, C.c_int32, c_ptr, c_ptr, c_ptr, C.c_float, C.c_float, C.c_float,

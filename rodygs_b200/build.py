@@ -35,6 +35,7 @@ SOURCES = {
     "sh_grad_views.cu": [],
     "loss.cu": [],
     "densify.cu": [],
+    "optim.cu": [],
 }
 HEADERS = ["common.cuh", "scene.cuh", os.path.join("..", "..", "include", "rodygs_b200.h")]
 

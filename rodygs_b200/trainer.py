@@ -12,6 +12,7 @@ gloo in the CPU tests).  Pose gradients and the means2D sink stay rank-local.
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -105,6 +106,26 @@ class SplatTrainStep:
         self.H, self.W, self.sh_degree = int(height), int(width), int(sh_degree)
         self.w = (float(w_l1), float(w_dssim), float(w_pearson), float(w_alpha))
         self.pg = process_group
+        self.optim: Dict[str, "GaussianAdam"] = {}
+        self.stats: Dict[str, "DensifyStats"] = {}
+        self._load_scene(scene)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.bg = torch.zeros(3, dtype=torch.float32, device=self.dev)          # rodygs.py:267
+        self.view_grad = torch.zeros(4, 4, **f32)
+        self.loss_parts = torch.zeros(8, **f32)   # [0:3] photometric (loss, l1, ssim), [3] pearson, [4] alpha term
+        self.dL_dcolor = torch.empty(3, self.H, self.W, **f32)
+        self.dL_ddepth = torch.zeros(1, self.H, self.W, **f32)
+        self.dL_dalpha = torch.zeros(1, self.H, self.W, **f32)
+        lib = _lib.load()
+        self._ws_bytes = int(lib.rdg_l1_dssim_workspace_bytes(3, self.H, self.W))
+        self._loss_ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.dev)
+        self.views_per_rank = 1
+        self.last_state: Optional[engine.FwdState] = None
+        self.stage_events = None   # set by enable_stage_timing()
+
+    def _load_scene(self, scene: Dict):
+        """(Re)build everything whose size depends on the Gaussian counts: the flat parameter / gradient buffers, the
+        birth-frame CSR, the per-Gaussian scratch.  Called by __init__ and after every densification."""
         ns, nd = scene["static"]["xyz"].shape[0], scene["dynamic"]["xyz"].shape[0]
         self.ns, self.nd = ns, nd
         self.num_basis = scene["motion_coeff"].shape[-1]
@@ -121,21 +142,10 @@ class SplatTrainStep:
         self.spatial_lr_scale = float(scene["spatial_lr_scale"])
         self.frame_order, self.frame_offsets = engine.frame_csr(self.time_ind, self.T) if nd > 0 else (None, None)
         self._g7 = torch.empty(max(nd, 1), 8, dtype=torch.float32, device=self.dev)
-        self.bg = torch.zeros(3, dtype=torch.float32, device=self.dev)          # rodygs.py:267
-        n = ns + nd
-        f32 = dict(dtype=torch.float32, device=self.dev)
-        self.means2D_grad = torch.zeros(n, 3, **f32)
-        self.view_grad = torch.zeros(4, 4, **f32)
-        self.loss_parts = torch.zeros(8, **f32)   # [0:3] photometric (loss, l1, ssim), [3] pearson, [4] alpha term
-        self.dL_dcolor = torch.empty(3, self.H, self.W, **f32)
-        self.dL_ddepth = torch.zeros(1, self.H, self.W, **f32)
-        self.dL_dalpha = torch.zeros(1, self.H, self.W, **f32)
-        lib = _lib.load()
-        self._ws_bytes = int(lib.rdg_l1_dssim_workspace_bytes(3, self.H, self.W))
-        self._loss_ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.dev)
-        self.views_per_rank = 1
-        self.last_state: Optional[engine.FwdState] = None
-        self.stage_events = None   # set by enable_stage_timing()
+        self.means2D_grad = torch.zeros(ns + nd, 3, dtype=torch.float32, device=self.dev)
+        if hasattr(self, "_grads_tmp"):
+            del self._grads_tmp
+        self.last_state = None
 
     # -- views into the flat buffers --------------------------------------------------------
     def _slice(self, buf: torch.Tensor, name: str) -> torch.Tensor:
@@ -267,6 +277,7 @@ class SplatTrainStep:
         n = self.ns + self.nd
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.views_per_rank, self.world_size = int(views_per_rank), int(world_size)
+        self._fx_args = (views_per_rank, world_size, copy_engine_gather, gather_streams)
         v_total = self.views_per_rank * self.world_size
         self._symm = None
         self.dcolor_all = None
@@ -358,6 +369,98 @@ class SplatTrainStep:
                                     ptr(self.dcolor_all), 1.0 / v_total, C.byref(gst), C.byref(gdy), _lib.stream_ptr()))
         cur.wait_event(self._ev_reduced)
         self._mark("exchange")
+
+    # -- optimiser, densification ------------------------------------------------
+    def _group_ranges(self, tag: str) -> Dict[str, Tuple[int, int]]:
+        """reference group name -> (float offset, numel) of model `tag` inside the flat buffers."""
+        from .optim import GROUP_OF
+        out = {}
+        for field, group in GROUP_OF.items():
+            off, shp = self.layout[f"{tag}.{field}"]
+            out[group] = (off, math.prod(shp))
+        if tag == "dynamic":
+            off, shp = self.layout["motion_coeff"]
+            out["motion_coeff"] = (off, math.prod(shp))
+        return out
+
+    def attach_optimizer(self, tag: str, lrs) -> "GaussianAdam":
+        """optim_setup (+ append_motion_optim for the dynamic model): rodygs_static.py:106-141, rodygs_dynamic.py:92-123."""
+        from .optim import GaussianAdam
+        opt = GaussianAdam(self._group_ranges(tag), self.params.numel(), lrs, self.spatial_lr_scale, self.dev)
+        self.optim[tag] = opt
+        return opt
+
+    def optimizer_step(self, tag: str, iteration: int, grad_scale: float = 1.0):
+        """current_gs.update_learning_rate(iteration); current_gs.optimizer.step() (rodygs.py:209,364)."""
+        return self.optim[tag].step(self.params, self.grads, iteration, grad_scale)
+
+    def enable_densification(self, tag: str):
+        from .densify import DensifyStats
+        self.stats[tag] = DensifyStats(self.ns if tag == "static" else self.nd, self.dev)
+        return self.stats[tag]
+
+    def add_densification_stats(self, tag: str):
+        """rodygs.py:319-341 after a backward pass: the radii and the means2D gradient sink of the half being trained."""
+        radii = self.last_outputs[3]
+        self.stats[tag].add(radii, self.means2D_grad, 0 if tag == "static" else self.ns)
+
+    def _model_tensors(self, tag: str):
+        from .optim import GROUP_OF
+        params = {g: self.p(f"{tag}.{f}") for f, g in GROUP_OF.items()}
+        if tag == "dynamic":
+            params["motion_coeff"] = self.p("motion_coeff")
+        return params
+
+    def densify_and_prune(self, tag: str, grad_threshold: float, min_opacity: float, extent: float,
+                          max_screen_size: Optional[float], percent_dense: float = 0.01, noise=None, generator=None):
+        """current_gs.densify_and_prune(...) (rodygs.py:343-356) on model `tag`; the flat buffers, the optimiser
+        moments, the statistics and the birth-frame table are rebuilt for the new Gaussian count.  Under data
+        parallelism every rank calls this with all-reduced statistics and the same noise."""
+        from . import densify as dn
+        from .optim import GROUP_OF
+        if tag in self.stats and self.pg is not None:
+            self.stats[tag].all_reduce(self.pg)
+        params = self._model_tensors(tag)
+        opt = self.optim.get(tag)
+        moments = {g: opt.moments(g) for g in params} if opt is not None else None
+        moments = {g: (m.view(params[g].shape), v.view(params[g].shape)) for g, (m, v) in moments.items()} if moments else None
+        extras = {"time_ind": self.time_ind} if tag == "dynamic" else None
+        new_p, new_m, new_e, new_stats, info = dn.densify_and_prune(params, moments, extras, self.stats[tag], grad_threshold,
+                                                                    min_opacity, extent, max_screen_size, percent_dense,
+                                                                    noise=noise, generator=generator)
+        other = "dynamic" if tag == "static" else "static"
+        inv = {g: f for f, g in GROUP_OF.items()}
+        scene = {tag: {inv[g]: t for g, t in new_p.items() if g in inv},
+                 other: {k: self.p(f"{other}.{k}") for k in PARAM_ORDER},
+                 "motion_coeff": new_p["motion_coeff"] if tag == "dynamic" else self.p("motion_coeff"),
+                 "table": self.p("table"), "time_ind": new_e["time_ind"] if tag == "dynamic" else self.time_ind,
+                 "spatial_lr_scale": self.spatial_lr_scale}
+        old_moments = {}
+        for t, o in self.optim.items():
+            old_moments[t] = {g: o.moments(g) for g in o.ranges} if t != tag else \
+                {g: (m.reshape(-1), v.reshape(-1)) for g, (m, v) in new_m.items()}
+        old_stats = {t: st for t, st in self.stats.items() if t != tag}
+        self._load_scene(scene)
+        from .optim import GaussianAdam
+        for t, o in list(self.optim.items()):
+            fresh = GaussianAdam(self._group_ranges(t), self.params.numel(), o.lrs, self.spatial_lr_scale, self.dev, o.betas, o.eps)
+            fresh.steps = o.steps
+            for g, (m, v) in old_moments[t].items():
+                fm, fv = fresh.moments(g)
+                fm.copy_(m)
+                fv.copy_(v)
+            self.optim[t] = fresh
+        self.stats = dict(old_stats)
+        self.stats[tag] = new_stats
+        if getattr(self, "_fx_args", None) is not None:          # the exchange buffers are sized by the Gaussian count
+            self.enable_factored_exchange(*self._fx_args)
+        return info
+
+    def reset_opacity(self, tag: str, cap: float = 0.01):
+        """current_gs.reset_opacity() (rodygs.py:358-362)."""
+        from . import densify as dn
+        opt = self.optim.get(tag)
+        dn.reset_opacity(self.p(f"{tag}.opacity"), opt.moments("opacity") if opt is not None else None, cap)
 
     def total_loss(self) -> torch.Tensor:
         """photometric + w_p * pearson + alpha term (device scalar)."""
