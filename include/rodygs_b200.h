@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RDG_ABI_VERSION 4
+#define RDG_ABI_VERSION 5
 #define RDG_TILE 16
 #define RDG_NUM_BASIS_MAX 16
 
@@ -321,6 +321,60 @@ int rdg_densify_apply(int64_t n_new, const uint32_t* map, const int32_t* split_r
 /* reset_opacity (src/trainer/rodygs_static.py:150-159): opacity = inverse_sigmoid(min(sigmoid(opacity), cap)),
  * Adam moments of the group zeroed (src/trainer/utils.py:15-32; may be NULL). */
 int rdg_reset_opacity(int64_t n, float* opacity, float cap, float* exp_avg, float* exp_avg_sq, void* stream);
+
+/* ---- motion regularisers ------------------------------------------------------- */
+
+/* MotionL1Loss + MotionSparsityLoss (src/trainer/losses.py:364-379) over coeff [n, num_basis] (= _motion_coeff
+ * [n, 1, num_basis]) in one pass.  loss_parts[0] = mean |c|, loss_parts[1] = mean(|c| / (max_b |c| + 1e-7)).
+ * d_coeff (may be NULL) receives w_l1 * dL1/dc + w_sparsity * dSparsity/dc; added to its contents when accumulate != 0.
+ * workspace: 16 bytes (two doubles), 8-byte aligned. */
+int rdg_motion_coeff_reg(int64_t n, int32_t num_basis, const float* coeff, float w_l1, float w_sparsity,
+                         float* loss_parts, float* d_coeff, int32_t accumulate, void* workspace, void* stream);
+
+/* MotionBasisRegularizaiton.forward (src/trainer/losses.py:499-525) on table [num_times, num_basis, 7], degree 0
+ * (velocity; every reference config) or negative (term disabled).  loss_parts[0] = translation term,
+ * loss_parts[1] = rotation term = mean(reg_coeff[b] * || I - (R(q[t+1]) - R(q[t])) ||_F) - the reference differences the
+ * rotation MATRICES (derivate_motion never passes is_rot, :493-497).  reg_coeff [num_basis]: the normalised weights of
+ * coeff_bank[freq_div_mode] (:387-489).  d_table (may be NULL) += grad_scale * dLoss/dtable.  workspace as above. */
+int rdg_motion_basis_reg(int32_t num_times, int32_t num_basis, const float* table, const float* reg_coeff,
+                         int32_t transl_degree, int32_t rot_degree, float grad_scale, float* loss_parts,
+                         float* d_table, void* workspace, void* stream);
+
+/* pytorch3d.ops.knn_points(p[None], p[None], K) of src/trainer/losses.py:238-239: for each of the n points the K
+ * nearest of the same n points (itself included), squared distances ascending; exact (grid search with a proven
+ * stopping rule, not approximate); exact ties towards the lower index.  idx [n, K] int32, dist2 [n, K].
+ * No host synchronisation; workspace 256-byte aligned, rdg_knn_workspace_bytes(n) bytes. */
+int64_t rdg_knn_workspace_bytes(int64_t n);
+int rdg_knn(int64_t n, const float* points, int32_t K, int32_t* idx, float* dist2, void* workspace,
+            int64_t workspace_bytes, void* stream);
+
+/* RigidityLoss.forward, modes "surface" and "distance_preserving" (src/trainer/losses.py:216-361), value and
+ * gradient.  The n rows are the reference's random sample (`indice`, :228-232) gathered by the caller:
+ *   points = (xyz + pred_translation)[indice], canon = xyz[indice], coeff = _motion_coeff[indice],
+ *   frame_indices = the torch.randint draw of :297-301, nn_idx / nn_dist2 = rdg_knn(points, K).
+ * loss_parts[0] = surface term, loss_parts[1] = distance-preserving term (the loss is their sum).
+ * d_points / d_canon / d_coeff are overwritten with the gradient of that sum; d_table [num_times, num_basis, 7] is
+ * added to (rows frame_indices, columns 0..2).  Mode "coeff" (no reference config uses it) is not built. */
+typedef struct RdgRigidity {
+    int64_t n;
+    int32_t K, num_basis, n_frames;
+    int32_t mode_surface, mode_distance;
+    float eps;                        /* CharbonnierLoss eps, 1e-6 */
+    const float* points;              /* [n, 3] */
+    const float* canon;               /* [n, 3] */
+    const float* coeff;               /* [n, num_basis] */
+    const float* table;               /* [num_times, num_basis, 7] */
+    const int32_t* frame_indices;     /* [n_frames] */
+    const int32_t* nn_idx;            /* [n, K] */
+    const float* nn_dist2;            /* [n, K] */
+    float* loss_parts;                /* [2] */
+    float* d_points;                  /* [n, 3] */
+    float* d_canon;                   /* [n, 3] */
+    float* d_coeff;                   /* [n, num_basis] */
+    float* d_table;                   /* [num_times, num_basis, 7], accumulated */
+} RdgRigidity;
+int64_t rdg_rigidity_workspace_bytes(int64_t n, int32_t K, int32_t n_frames);
+int rdg_rigidity(const RdgRigidity* args, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,14 @@ class RdgLossTerms(C.Structure):
                 ("dL_ddepth", c_ptr), ("alpha", c_ptr), ("w_alpha", C.c_float), ("dL_dalpha", c_ptr)]
 
 
+class RdgRigidity(C.Structure):
+    _fields_ = [("n", C.c_int64), ("K", C.c_int32), ("num_basis", C.c_int32), ("n_frames", C.c_int32),
+                ("mode_surface", C.c_int32), ("mode_distance", C.c_int32), ("eps", C.c_float),
+                ("points", c_ptr), ("canon", c_ptr), ("coeff", c_ptr), ("table", c_ptr), ("frame_indices", c_ptr),
+                ("nn_idx", c_ptr), ("nn_dist2", c_ptr), ("loss_parts", c_ptr), ("d_points", c_ptr), ("d_canon", c_ptr),
+                ("d_coeff", c_ptr), ("d_table", c_ptr)]
+
+
 # every symbol include/rodygs_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "rdg_abi_version": (C.c_int, []),
@@ -114,6 +122,14 @@ SYMBOLS = {
     "rdg_densify_apply": (C.c_int, [C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, C.POINTER(RdgDensifyField), C.c_int32, c_ptr,
                                     c_ptr, C.c_int32, c_ptr, c_ptr]),
     "rdg_reset_opacity": (C.c_int, [C.c_int64, c_ptr, C.c_float, c_ptr, c_ptr, c_ptr]),
+    "rdg_motion_coeff_reg": (C.c_int, [C.c_int64, C.c_int32, c_ptr, C.c_float, C.c_float, c_ptr, c_ptr, C.c_int32, c_ptr,
+                                       c_ptr]),
+    "rdg_motion_basis_reg": (C.c_int, [C.c_int32, C.c_int32, c_ptr, c_ptr, C.c_int32, C.c_int32, C.c_float, c_ptr, c_ptr,
+                                       c_ptr, c_ptr]),
+    "rdg_knn_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "rdg_knn": (C.c_int, [C.c_int64, c_ptr, C.c_int32, c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr]),
+    "rdg_rigidity_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "rdg_rigidity": (C.c_int, [C.POINTER(RdgRigidity), c_ptr, C.c_int64, c_ptr]),
 }
 
 _lib = None
@@ -133,7 +149,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.rdg_abi_version() != 4:
+    if lib.rdg_abi_version() != 5:
         raise RuntimeError("librodygs_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -36,6 +36,9 @@ SOURCES = {
     "loss.cu": [],
     "densify.cu": [],
     "optim.cu": [],
+    "motion_reg.cu": [],
+    "knn.cu": ["-fmad=false"],
+    "rigidity.cu": [],
 }
 HEADERS = ["common.cuh", "scene.cuh", os.path.join("..", "..", "include", "rodygs_b200.h")]
 
