@@ -376,6 +376,20 @@ typedef struct RdgRigidity {
 int64_t rdg_rigidity_workspace_bytes(int64_t n, int32_t K, int32_t n_frames);
 int rdg_rigidity(const RdgRigidity* args, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Flat-buffer trainer glue for RigidityLoss: gather the sampled rows (`indice` [n] int32, no repeats - random.sample,
+ * losses.py:228-232) and deform them, points = xyz[i] + spatial_lr_scale * sum_b c_ib (basis_t_b - table[time_ind[i]]_b)[:3]
+ * (src/model/rodygs_dynamic.py:122-138), canon = xyz[i], coeff_s = coeff[i]; the fused render path never materialises
+ * pred_translation. */
+int rdg_rigidity_sample(int64_t n, int32_t num_basis, const int32_t* indice, const float* xyz, const float* coeff,
+                        const int32_t* time_ind, const float* basis_t, const float* table, float spatial_lr_scale,
+                        float* points, float* canon, float* coeff_s, void* stream);
+/* ... and its backward: grad_scale * (d_points, d_canon, d_coeff_s of rdg_rigidity; the last two may be NULL) is ADDED to
+ * the rows `indice` of d_xyz / d_coeff and, through the deformation, to d_basis_t [num_basis, 7] and d_table. */
+int rdg_rigidity_sample_bwd(int64_t n, int32_t num_basis, int32_t num_times, const int32_t* indice, const float* coeff,
+                            const int32_t* time_ind, const float* basis_t, const float* table, float spatial_lr_scale,
+                            float grad_scale, const float* d_points, const float* d_canon, const float* d_coeff_s,
+                            float* d_xyz, float* d_coeff, float* d_basis_t, float* d_table, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

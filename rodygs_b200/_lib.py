@@ -130,6 +130,10 @@ SYMBOLS = {
     "rdg_knn": (C.c_int, [C.c_int64, c_ptr, C.c_int32, c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr]),
     "rdg_rigidity_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
     "rdg_rigidity": (C.c_int, [C.POINTER(RdgRigidity), c_ptr, C.c_int64, c_ptr]),
+    "rdg_rigidity_sample": (C.c_int, [C.c_int64, C.c_int32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_float, c_ptr, c_ptr,
+                                      c_ptr, c_ptr]),
+    "rdg_rigidity_sample_bwd": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_float,
+                                          C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
 }
 
 _lib = None

@@ -323,3 +323,129 @@ extern "C" int rdg_rigidity(const RdgRigidity* a, void* workspace, int64_t works
     rdg_count_launches(launches);
     return RDG_OK;
 }
+
+// ---- sample gather / scatter for the flat-buffer trainer ---------------------------------------------------------------
+// The reference draws `indice` (losses.py:228-232) and indexes xyz + pred_translation, _motion_coeff with it; on the fused
+// path pred_translation is never materialised (it lives inside preprocess_fwd), so the sampled rows are deformed here:
+//   points_s = xyz[i] + lr * sum_b c_ib (B(t)_b - table[t_i]_b)[:3]         (src/model/rodygs_dynamic.py:122-138)
+// and the backward sends d_points / d_canon / d_coeff of the sample back to the rows of the full model, to B(t) and to the
+// table.  d_table is reduced per birth frame in shared memory first (T x 16 x 3 floats), flushed once per CTA; B(t)'s
+// gradient is minus the sum of the table's over the frames, taken from the same accumulators.
+
+__global__ void __launch_bounds__(RG_BLOCK) rg_sample_fwd_kernel(int64_t n, const int32_t* __restrict__ indice,
+                                                                 const float* __restrict__ xyz, const float* __restrict__ coeff,
+                                                                 const int32_t* __restrict__ time_ind,
+                                                                 const float* __restrict__ basis_t, const float* __restrict__ table,
+                                                                 float lr, float* __restrict__ points, float* __restrict__ canon,
+                                                                 float* __restrict__ coeff_s) {
+    const int64_t s = (int64_t)blockIdx.x * RG_BLOCK + threadIdx.x;
+    if (s >= n) return;
+    const int64_t i = indice[s];
+    float c[RG_B];
+    load_coeff(coeff, i, c);
+    const float* row = table + (int64_t)time_ind[i] * RG_B * 7;
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+#pragma unroll
+    for (int b = 0; b < RG_B; ++b) {
+        tx += c[b] * (basis_t[b * 7] - row[b * 7]);
+        ty += c[b] * (basis_t[b * 7 + 1] - row[b * 7 + 1]);
+        tz += c[b] * (basis_t[b * 7 + 2] - row[b * 7 + 2]);
+    }
+    const float x = xyz[i * 3], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
+    canon[s * 3] = x; canon[s * 3 + 1] = y; canon[s * 3 + 2] = z;
+    points[s * 3] = x + tx * lr; points[s * 3 + 1] = y + ty * lr; points[s * 3 + 2] = z + tz * lr;
+    float4* dst = reinterpret_cast<float4*>(coeff_s + s * RG_B);
+#pragma unroll
+    for (int k = 0; k < RG_B / 4; ++k) dst[k] = make_float4(c[4 * k], c[4 * k + 1], c[4 * k + 2], c[4 * k + 3]);
+}
+
+__global__ void __launch_bounds__(RG_BLOCK) rg_sample_bwd_kernel(int64_t n, int T, const int32_t* __restrict__ indice,
+                                                                 const float* __restrict__ coeff, const int32_t* __restrict__ time_ind,
+                                                                 const float* __restrict__ basis_t, const float* __restrict__ table,
+                                                                 float lr, float scale, const float* __restrict__ d_points,
+                                                                 const float* __restrict__ d_canon, const float* __restrict__ d_coeff_s,
+                                                                 float* __restrict__ d_xyz, float* __restrict__ d_coeff,
+                                                                 float* __restrict__ d_basis_t, float* __restrict__ d_table) {
+    extern __shared__ float sT[];                    // [T][RG_B][3]: sum of lr * scale * c_ib * g_i over the CTA's rows
+    for (int e = threadIdx.x; e < T * RG_B * 3; e += RG_BLOCK) sT[e] = 0.f;
+    __syncthreads();
+    for (int64_t s = (int64_t)blockIdx.x * RG_BLOCK + threadIdx.x; s < n; s += (int64_t)gridDim.x * RG_BLOCK) {
+        const int64_t i = indice[s];                 // the sample has no repeated rows (random.sample): plain read-modify-write
+        const float gx = d_points[s * 3], gy = d_points[s * 3 + 1], gz = d_points[s * 3 + 2];
+        d_xyz[i * 3] += scale * (gx + (d_canon ? d_canon[s * 3] : 0.f));
+        d_xyz[i * 3 + 1] += scale * (gy + (d_canon ? d_canon[s * 3 + 1] : 0.f));
+        d_xyz[i * 3 + 2] += scale * (gz + (d_canon ? d_canon[s * 3 + 2] : 0.f));
+        float c[RG_B];
+        load_coeff(coeff, i, c);
+        const int t = time_ind[i];
+        const float* row = table + (int64_t)t * RG_B * 7;
+        float* acc = sT + t * RG_B * 3;
+        float4* dst = reinterpret_cast<float4*>(d_coeff + i * RG_B);
+        const float4* dcs = d_coeff_s ? reinterpret_cast<const float4*>(d_coeff_s + s * RG_B) : nullptr;
+        const float k = lr * scale;
+#pragma unroll
+        for (int q = 0; q < RG_B / 4; ++q) {
+            float4 o = dst[q];
+            float add[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int b = 4 * q + e;
+                add[e] = k * ((basis_t[b * 7] - row[b * 7]) * gx + (basis_t[b * 7 + 1] - row[b * 7 + 1]) * gy +
+                              (basis_t[b * 7 + 2] - row[b * 7 + 2]) * gz);
+                atomicAdd(acc + b * 3, k * c[b] * gx);
+                atomicAdd(acc + b * 3 + 1, k * c[b] * gy);
+                atomicAdd(acc + b * 3 + 2, k * c[b] * gz);
+            }
+            if (dcs) {
+                const float4 v = dcs[q];
+                add[0] += scale * v.x; add[1] += scale * v.y; add[2] += scale * v.z; add[3] += scale * v.w;
+            }
+            o.x += add[0]; o.y += add[1]; o.z += add[2]; o.w += add[3];
+            dst[q] = o;
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < T * RG_B * 3; e += RG_BLOCK) {
+        const float v = sT[e];
+        if (v != 0.f) {
+            const int t = e / (RG_B * 3), rem = e % (RG_B * 3), b = rem / 3, d = rem % 3;
+            atomicAdd(d_table + ((int64_t)t * RG_B + b) * 7 + d, -v);
+            atomicAdd(d_basis_t + b * 7 + d, v);
+        }
+    }
+}
+
+extern "C" int rdg_rigidity_sample(int64_t n, int32_t num_basis, const int32_t* indice, const float* xyz, const float* coeff,
+                                   const int32_t* time_ind, const float* basis_t, const float* table, float spatial_lr_scale,
+                                   float* points, float* canon, float* coeff_s, void* stream) {
+    RDG_CHECK_ARG(n > 0 && indice && xyz && coeff && time_ind && basis_t && table && points && canon && coeff_s, "null argument");
+    RDG_CHECK_ARG(num_basis == RG_B, "only num_basis == 16 (the reference's configs) is built");
+    RDG_CHECK_ARG((((uintptr_t)coeff | (uintptr_t)coeff_s) & 15) == 0, "coeff buffers must be 16-byte aligned");
+    rg_sample_fwd_kernel<<<rdg_div_up(n, RG_BLOCK), RG_BLOCK, 0, (cudaStream_t)stream>>>(
+        n, indice, xyz, coeff, time_ind, basis_t, table, spatial_lr_scale, points, canon, coeff_s);
+    RDG_CHECK_LAUNCH();
+    rdg_count_launches(1);
+    return RDG_OK;
+}
+
+extern "C" int rdg_rigidity_sample_bwd(int64_t n, int32_t num_basis, int32_t num_times, const int32_t* indice, const float* coeff,
+                                       const int32_t* time_ind, const float* basis_t, const float* table, float spatial_lr_scale,
+                                       float grad_scale, const float* d_points, const float* d_canon, const float* d_coeff_s,
+                                       float* d_xyz, float* d_coeff, float* d_basis_t, float* d_table, void* stream) {
+    RDG_CHECK_ARG(n > 0 && indice && coeff && time_ind && basis_t && table && d_points && d_xyz && d_coeff && d_basis_t && d_table,
+                  "null argument");
+    RDG_CHECK_ARG(num_basis == RG_B, "only num_basis == 16 (the reference's configs) is built");
+    RDG_CHECK_ARG((((uintptr_t)coeff | (uintptr_t)d_coeff | (uintptr_t)d_coeff_s) & 15) == 0, "coeff buffers must be 16-byte aligned");
+    const size_t smem = (size_t)num_times * RG_B * 3 * 4;
+    RDG_CHECK_ARG(num_times >= 1 && smem <= 160 * 1024, "1 <= num_times <= 853");
+    if (smem > 48 * 1024)
+        RDG_CUDA(cudaFuncSetAttribute(rg_sample_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t want = (n + RG_BLOCK - 1) / RG_BLOCK;
+    const int grid = (int)(want < (int64_t)RDG_SM_COUNT * 2 ? want : (int64_t)RDG_SM_COUNT * 2);
+    rg_sample_bwd_kernel<<<grid, RG_BLOCK, smem, (cudaStream_t)stream>>>(n, num_times, indice, coeff, time_ind, basis_t, table,
+                                                                          spatial_lr_scale, grad_scale, d_points, d_canon, d_coeff_s,
+                                                                          d_xyz, d_coeff, d_basis_t, d_table);
+    RDG_CHECK_LAUNCH();
+    rdg_count_launches(1);
+    return RDG_OK;
+}

@@ -462,6 +462,69 @@ class SplatTrainStep:
         opt = self.optim.get(tag)
         dn.reset_opacity(self.p(f"{tag}.opacity"), opt.moments("opacity") if opt is not None else None, cap)
 
+    # -- motion regularisers --------------------------------------------------------
+    def motion_losses_backward(self, iteration: int, basis_t: torch.Tensor, w_motion_l1: float = 0.01,
+                               w_sparsity: float = 0.002, w_basis: float = 0.1, basis_mode: str = "cum_exponential",
+                               w_rigidity: float = 0.5, rigidity_freq: int = 5, K: int = 8, sample_scale: float = 2,
+                               dist_preserving_ratio: int = 4, indice: Optional[torch.Tensor] = None,
+                               frame_indices: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The dynamic model's regularisers of configs/train/*.yaml:198-237 (motion_l1_reg, motion_sparsity, rigidity
+        with freq 5, motion_basis_reg), each gated like MultiLoss.forward (losses.py:67-73: `iteration % freq == 0 and
+        iteration > start`, start 0), value + gradient in one C-ABI call each; the weighted gradients are ADDED to the
+        flat gradient buffer that forward_backward() has just written.  Returns motion_parts [6] on the device:
+        (mean|c|, sparsity, basis translation, basis rotation, rigidity surface, rigidity distance-preserving).
+        indice / frame_indices override the reference's random draws (tests)."""
+        from . import motion_reg as mr
+        import random
+        lib = _lib.load()
+        stream = _lib.stream_ptr()
+        parts = torch.zeros(6, dtype=torch.float32, device=self.dev)
+        if self.nd == 0 or iteration <= 0:
+            return parts
+        coeff = self.p("motion_coeff").view(self.nd, self.num_basis)
+        d_coeff = self.g("motion_coeff").view(self.nd, self.num_basis)
+        table, d_table = self.p("table"), self.g("table")
+        if w_motion_l1 != 0.0 or w_sparsity != 0.0:
+            parts[0:2] = mr.motion_coeff_reg_(coeff, w_motion_l1, w_sparsity, d_coeff, accumulate=True)
+        if w_basis != 0.0:
+            if getattr(self, "_basis_mode", None) != basis_mode:
+                self._basis_mode, self._basis_reg = basis_mode, mr.basis_reg_coeff(basis_mode).to(self.dev)
+            parts[2:4] = mr.motion_basis_reg_(table, self._basis_reg, 0, 0, d_table, grad_scale=w_basis)
+        if w_rigidity != 0.0 and iteration % rigidity_freq == 0:
+            scale = 1 / sample_scale if sample_scale > 1 else sample_scale
+            if indice is None:
+                indice = torch.tensor(random.sample(range(self.nd), int(self.nd * scale)))       # losses.py:228-232
+            if frame_indices is None:
+                frame_indices = torch.randint(0, self.T - 1, (self.T // dist_preserving_ratio,))   # :297-301
+            idx = indice.to(self.dev, torch.int32).contiguous()
+            fi = frame_indices.to(self.dev, torch.int32).contiguous()
+            n = idx.numel()
+            f32 = dict(dtype=torch.float32, device=self.dev)
+            pts, canon, cs = torch.empty(n, 3, **f32), torch.empty(n, 3, **f32), torch.empty(n, self.num_basis, **f32)
+            xyz = self.p("dynamic.xyz")
+            check(lib.rdg_rigidity_sample(n, self.num_basis, ptr(idx), ptr(xyz), ptr(coeff), ptr(self.time_ind), ptr(basis_t),
+                                          ptr(table), self.spatial_lr_scale, ptr(pts), ptr(canon), ptr(cs), stream))
+            d2, nn = mr.knn_points(pts, K)
+            a = _lib.RdgRigidity()
+            a.n, a.K, a.num_basis, a.n_frames, a.eps = n, K, self.num_basis, fi.numel(), 1e-6
+            a.mode_surface, a.mode_distance = 1, 1
+            d_pts, d_canon, d_cs = torch.empty_like(pts), torch.empty_like(canon), torch.empty_like(cs)
+            d_tab = torch.zeros_like(table) if w_rigidity != 1.0 else d_table
+            a.points, a.canon, a.coeff, a.table, a.frame_indices = ptr(pts), ptr(canon), ptr(cs), ptr(table), ptr(fi)
+            a.nn_idx, a.nn_dist2, a.loss_parts = ptr(nn), ptr(d2), parts[4:6].data_ptr()
+            a.d_points, a.d_canon, a.d_coeff, a.d_table = ptr(d_pts), ptr(d_canon), ptr(d_cs), ptr(d_tab)
+            nbytes = int(lib.rdg_rigidity_workspace_bytes(n, K, fi.numel()))
+            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.dev)
+            check(lib.rdg_rigidity(C.byref(a), ptr(ws), nbytes, stream))
+            if d_tab is not d_table:
+                d_table.add_(d_tab, alpha=w_rigidity)
+            check(lib.rdg_rigidity_sample_bwd(n, self.num_basis, self.T, ptr(idx), ptr(coeff), ptr(self.time_ind), ptr(basis_t),
+                                              ptr(table), self.spatial_lr_scale, float(w_rigidity), ptr(d_pts), ptr(d_canon),
+                                              ptr(d_cs), ptr(self.g("dynamic.xyz")), ptr(d_coeff), ptr(self.g("basis_t")),
+                                              ptr(d_table), stream))
+        self.motion_parts = parts
+        return parts
+
     def total_loss(self) -> torch.Tensor:
         """photometric + w_p * pearson + alpha term (device scalar)."""
         lp = self.loss_parts

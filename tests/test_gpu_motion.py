@@ -199,3 +199,47 @@ def test_rigidity_class_draws_like_the_reference():
     torch.manual_seed(99)
     loss = mr.RigidityLoss(K=int(g["K"]), mode=["distance_preserving", "surface"])(M(), pred_tr)
     _check("rigid_cfg", g, loss, {"xyz": xyz, "coeff": coeff, "table": table, "pred_tr": pred_tr})
+
+
+def test_trainer_motion_losses_add_reference_gradients():
+    """SplatTrainStep.motion_losses_backward on the flat buffers == the reference's weighted sum of the four
+    regularisers (configs/train/train_kubric_mrig.yaml:198-237) differentiated by autograd on the CPU, with
+    pred_translation = spatial_lr_scale * c . (B(t) - B(t_i))[:3] (rodygs_dynamic.py:122-138)."""
+    from rodygs_b200 import synthetic, trainer, motion_reg as mr
+    H, W, T = 64, 96, 12
+    sc = synthetic.make_scene(6000, H, W, T, seed=4, radius_px=4.0)
+    sc["spatial_lr_scale"] = 1.7
+    step = trainer.SplatTrainStep(sc, H, W)
+    nd = step.nd
+    gen = torch.Generator().manual_seed(8)
+    basis_t = (torch.randn(16, 7, generator=gen) * 0.05)
+    indice = torch.randperm(nd, generator=gen)[: nd // 2]
+    fi = torch.randint(0, T - 1, (T // 4,), generator=gen)
+    w = dict(w_motion_l1=0.01, w_sparsity=0.002, w_basis=0.1, w_rigidity=0.5)
+    # --- reference composition on the CPU ---
+    xyz = sc["dynamic"]["xyz"].clone().requires_grad_(True)
+    coeff = sc["motion_coeff"].clone().requires_grad_(True)          # [nd, 1, 16]
+    table = sc["table"].clone().requires_grad_(True)
+    bt = basis_t.clone().requires_grad_(True)
+    ti = sc["time_ind"].long()
+    delta = (coeff.squeeze(1)[:, :, None] * (bt[None] - table[ti])).sum(1)         # [nd, 7]
+    pred = delta[:, :3] * sc["spatial_lr_scale"]
+    rig, rparts = mo.rigidity(xyz, coeff, torch.zeros(nd, 1, 3), pred, table, indice, fi, K=8)
+    reg = mr.basis_reg_coeff("cum_exponential")
+    total = (w["w_motion_l1"] * mo.motion_l1(coeff) + w["w_sparsity"] * mo.motion_sparsity(coeff)
+             + w["w_basis"] * mo.motion_basis_reg(table, reg) + w["w_rigidity"] * rig)
+    gref = torch.autograd.grad(total, [xyz, coeff, table, bt])
+    # --- CUDA path: gradients are added to what the buffers hold ---
+    step.grads.fill_(0.0)
+    parts = step.motion_losses_backward(5, basis_t.cuda(), indice=indice, frame_indices=fi, **w)
+    assert abs(parts[0].item() - mo.motion_l1(coeff).item()) < 1e-6
+    assert abs(parts[4].item() - rparts["surface"].item()) < 1e-5
+    assert abs(parts[5].item() - rparts["distance_preserving"].item()) < 1e-5
+    got = [step.g("dynamic.xyz"), step.g("motion_coeff"), step.g("table"), step.g("basis_t")]
+    for name, a, b in zip(("xyz", "coeff", "table", "basis_t"), got, gref):
+        assert rel_err(a.cpu().reshape(b.shape), b) < GRAD_TOL, (name, rel_err(a.cpu().reshape(b.shape), b))
+    # rigidity is skipped off its frequency (MultiLoss gating), the other three still run
+    step.grads.fill_(0.0)
+    parts = step.motion_losses_backward(6, basis_t.cuda(), indice=indice, frame_indices=fi, **w)
+    assert parts[4].item() == 0 and parts[5].item() == 0 and parts[0].item() > 0
+    assert step.g("dynamic.xyz").abs().max().item() == 0
