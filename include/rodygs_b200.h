@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RDG_ABI_VERSION 5
+#define RDG_ABI_VERSION 6
 #define RDG_TILE 16
 #define RDG_NUM_BASIS_MAX 16
 
@@ -389,6 +389,44 @@ int rdg_rigidity_sample_bwd(int64_t n, int32_t num_basis, int32_t num_times, con
                             const int32_t* time_ind, const float* basis_t, const float* table, float spatial_lr_scale,
                             float grad_scale, const float* d_points, const float* d_canon, const float* d_coeff_s,
                             float* d_xyz, float* d_coeff, float* d_basis_t, float* d_table, void* stream);
+
+/* ---- time embedding + motion-basis MLP ------------------------------------------- */
+
+/* TimestepEmbedder.forward (src/model/rodygs_dynamic.py:202-220) + MLPBasisNetwork.batch_inference / forward
+ * (:296-327) for a batch of `rows` times: timenet emb_dim -> width -> width -> width/2, then num_basis heads
+ * width/2 -> width/4 -> out_dim (7 = 3 translation + 4 rotation).  The trainer asks for rows = 1 + T (the query time t
+ * first, then the T training times), so B(t) [num_basis, 7] and the table [T, num_basis, 7] come from ONE launch.
+ *
+ * params: ONE packed fp32 buffer, PyTorch [out, in] row-major blocks in this order
+ *   timenet.0.weight [W,E] | timenet.0.bias [W] | timenet.2.weight [W,W] | timenet.2.bias [W] |
+ *   timenet.4.weight [W/2,W] | timenet.4.bias [W/2] |
+ *   basis_xyz.{k}.basis.0.weight stacked over k [nb,W/4,W/2] | ....basis.0.bias [nb,W/4] |
+ *   basis_xyz.{k}.basis.2.weight [nb,out,W/4] | ....basis.2.bias [nb,out]            (rdg_basis_mlp_param_count floats)
+ * Either `emb` [rows, emb_dim] (what batch_embedding, :290-294, returns) or `times` [rows] with `freqs_pi` [(emb_dim-1)/2]
+ * (= freq_bands * pi, :205-212) so that the embedding is evaluated in the kernel.
+ * saved (may be NULL for inference): [rows, rdg_basis_mlp_saved_floats()] the embedding and every pre-activation,
+ * the only state the backward needs.  activation: 0 = nn.GELU() (erf form), 1 = nn.ReLU. */
+typedef struct RdgBasisMlp {
+    int32_t emb_dim, width, num_basis, out_dim, activation, rows;
+    const float* params;
+    const float* emb;        /* [rows, emb_dim] or NULL */
+    const float* times;      /* [rows] (used when emb == NULL) */
+    const float* freqs_pi;   /* [(emb_dim - 1) / 2] */
+    float* basis;            /* out [rows, num_basis, out_dim] */
+    float* basis_row0;       /* NULL, or: row 0 goes here [num_basis, out_dim] and rows 1.. to basis[0 .. rows-2] - the
+                                trainer keeps B(t) and the table in different slices of its flat buffer */
+    float* saved;            /* out (fwd) / in (bwd) [rows, saved_floats] */
+} RdgBasisMlp;
+int64_t rdg_basis_mlp_param_count(int32_t emb_dim, int32_t width, int32_t num_basis, int32_t out_dim);
+int64_t rdg_basis_mlp_saved_floats(int32_t emb_dim, int32_t width, int32_t num_basis);
+int rdg_basis_mlp_fwd(const RdgBasisMlp* args, void* stream);
+/* Backward of the above (what loss.backward(), src/trainer/rodygs.py:310, runs through the MLP): d_basis
+ * [rows, num_basis, out_dim] -> d_params (packed like params; overwritten, or added to when accumulate != 0).
+ * d_basis_row0: NULL, or the gradient of row 0 (then d_basis holds rows 1.., like basis_row0 above).
+ * Two launches, no atomics: the result is deterministic.  args->basis is not read. */
+int64_t rdg_basis_mlp_bwd_workspace_bytes(int32_t rows, int32_t emb_dim, int32_t width, int32_t num_basis);
+int rdg_basis_mlp_bwd(const RdgBasisMlp* args, const float* d_basis, const float* d_basis_row0, float* d_params,
+                      int32_t accumulate, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,12 @@ class RdgLossTerms(C.Structure):
                 ("dL_ddepth", c_ptr), ("alpha", c_ptr), ("w_alpha", C.c_float), ("dL_dalpha", c_ptr)]
 
 
+class RdgBasisMlp(C.Structure):
+    _fields_ = [("emb_dim", C.c_int32), ("width", C.c_int32), ("num_basis", C.c_int32), ("out_dim", C.c_int32),
+                ("activation", C.c_int32), ("rows", C.c_int32), ("params", c_ptr), ("emb", c_ptr), ("times", c_ptr),
+                ("freqs_pi", c_ptr), ("basis", c_ptr), ("basis_row0", c_ptr), ("saved", c_ptr)]
+
+
 class RdgRigidity(C.Structure):
     _fields_ = [("n", C.c_int64), ("K", C.c_int32), ("num_basis", C.c_int32), ("n_frames", C.c_int32),
                 ("mode_surface", C.c_int32), ("mode_distance", C.c_int32), ("eps", C.c_float),
@@ -134,6 +140,11 @@ SYMBOLS = {
                                       c_ptr, c_ptr]),
     "rdg_rigidity_sample_bwd": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_float,
                                           C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "rdg_basis_mlp_param_count": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "rdg_basis_mlp_saved_floats": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "rdg_basis_mlp_fwd": (C.c_int, [C.POINTER(RdgBasisMlp), c_ptr]),
+    "rdg_basis_mlp_bwd_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "rdg_basis_mlp_bwd": (C.c_int, [C.POINTER(RdgBasisMlp), c_ptr, c_ptr, c_ptr, C.c_int32, c_ptr, C.c_int64, c_ptr]),
 }
 
 _lib = None
@@ -153,7 +164,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.rdg_abi_version() != 5:
+    if lib.rdg_abi_version() != 6:
         raise RuntimeError("librodygs_b200.so ABI version mismatch")
     _lib = lib
     return lib

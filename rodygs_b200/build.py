@@ -39,6 +39,7 @@ SOURCES = {
     "motion_reg.cu": [],
     "knn.cu": ["-fmad=false"],
     "rigidity.cu": [],
+    "basis_mlp.cu": [],
 }
 HEADERS = ["common.cuh", "scene.cuh", os.path.join("..", "..", "include", "rodygs_b200.h")]
 

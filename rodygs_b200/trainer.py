@@ -370,6 +370,46 @@ class SplatTrainStep:
         cur.wait_event(self._ev_reduced)
         self._mark("exchange")
 
+    # -- motion-basis MLP ----------------------------------------------------------------
+    def attach_basis_mlp(self, mlp, train_times: torch.Tensor, lr: float = 0.0):
+        """mlp: rodygs_b200.deform.BasisMLP.  train_times [T]: the dataset's normalised frame times, whose
+        embeddings the reference caches as `_time_batch_embeddings` (rodygs_dynamic.py:58-77).  After this,
+        basis_forward(t) fills B(t) and the table of the flat PARAMETER buffer straight from the network and
+        basis_backward() turns their gradients into the network's packed parameter gradient."""
+        assert train_times.numel() == self.T, "one training time per table row"
+        self.mlp = mlp
+        self._mlp_times = torch.cat((torch.zeros(1), train_times.detach().float().cpu().reshape(-1))).to(self.dev)
+        self._mlp_lr = float(lr)
+        self._mlp_moments = None
+        return mlp
+
+    def basis_forward(self, t) -> torch.Tensor:
+        """One launch: B(t) -> p("basis_t"), B(t_i) for all training times -> p("table")
+        (get_gaussian_deformation + get_total_motion_table, rodygs_dynamic.py:122-147).  Returns the B(t) slice,
+        which is what forward_backward(basis_t=...) takes.  t: python float or 0-d tensor (no host sync either way)."""
+        if torch.is_tensor(t):
+            self._mlp_times[0:1].copy_(t.reshape(1), non_blocking=True)
+        else:
+            self._mlp_times[0:1].fill_(float(t))
+        self.mlp.forward_rows(times=self._mlp_times, out=self.p("table"), out_row0=self.p("basis_t"))
+        return self.p("basis_t")
+
+    def basis_backward(self, accumulate: bool = False) -> torch.Tensor:
+        """dL/dB(t) and dL/dtable of the flat GRADIENT buffer -> mlp.grad (two launches, deterministic)."""
+        return self.mlp.backward_rows(self.g("table"), d_row0=self.g("basis_t"), accumulate=accumulate)
+
+    def basis_optimizer_step(self, iteration: int, grad_scale: float = 1.0):
+        """Adam step of the "deform_network" group (append_motion_optim, src/trainer/rodygs_dynamic.py:101-106: one group,
+        eps 1e-15) on the packed buffer - one rdg_adam launch.  The learning rate is constant = deform_lr_init:
+        update_learning_rate (:199-213) looks for a group named "deform", which does not exist, so the exponential
+        schedule built at :118-123 is never applied."""
+        mlp = self.mlp
+        if self._mlp_moments is None:
+            self._mlp_moments = (torch.zeros_like(mlp.grad), torch.zeros_like(mlp.grad))
+        m, v = self._mlp_moments
+        check(_lib.load().rdg_adam(ptr(mlp.params), ptr(mlp.grad), ptr(m), ptr(v), mlp.params.numel(), self._mlp_lr, 0.9, 0.999,
+                                   1e-15, int(iteration), float(grad_scale), _lib.stream_ptr()))
+
     # -- optimiser, densification (SURVEY.md §8 f1 / f2) ------------------------------------------------
     def _group_ranges(self, tag: str) -> Dict[str, Tuple[int, int]]:
         """reference group name -> (float offset, numel) of model `tag` inside the flat buffers."""

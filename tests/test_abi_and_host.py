@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/rodygs_b200.h but not exported"
         assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype in rodygs_b200/_lib.py"
     assert set(_lib.SYMBOLS) == set(declared)
-    assert lib.rdg_abi_version() == 5
+    assert lib.rdg_abi_version() == 6
     assert isinstance(lib.rdg_launch_count(), int)
 
 
