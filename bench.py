@@ -329,6 +329,31 @@ def run_ours(args, rank, world, local_rank):
         one_step(k, e2e=True)
     ms_e2e = timed(args.steps, e2e=True)
 
+    # ---- the motion-basis MLP (row a1), timed on its own: the scene's table is a stand-in for its output
+    # (SURVEY.md §8d), so the network runs beside the step, not inside it ----
+    mlp_info = None
+    if not args.forward_only:
+        from rodygs_b200 import deform
+        mlp = step.attach_basis_mlp(deform.BasisMLP(128, 16, 26, False, device=dev), torch.arange(T, dtype=torch.float32) / T)
+        keep_table, keep_bt = step.p("table").clone(), step.p("basis_t").clone()
+        l0 = int(lib.rdg_launch_count())
+        for _ in range(3):
+            step.basis_forward(0.37)
+            step.basis_backward()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        for k in range(args.steps):
+            step.basis_forward(0.01 * k)
+            step.basis_backward()
+        ev1.record()
+        torch.cuda.synchronize()
+        mlp_info = {"ms_fwd_bwd": ev0.elapsed_time(ev1) / args.steps, "rows": T + 1, "params": mlp.n_params,
+                    "launches_per_step": (int(lib.rdg_launch_count()) - l0) // (args.steps + 3),
+                    "note": "rdg_basis_mlp_fwd + _bwd for B(t) and the T-row table; not part of ms_per_step"}
+        step.p("table").copy_(keep_table)
+        step.p("basis_t").copy_(keep_bt)
+
     # ---- per-stage device times from the events recorded inside the timed region ----
     stage_ms = {}
     prev = None
@@ -398,6 +423,7 @@ def run_ours(args, rank, world, local_rank):
                               "frac": total_bytes / (ms_step * 1e-3) / 1e9 / peak,
                               "note": "whole step (all kernels + launch gaps) against the HBM peak"},
             "stage_ms": stage_ms,
+            "basis_mlp": mlp_info,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

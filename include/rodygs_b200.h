@@ -122,6 +122,9 @@ typedef struct RdgBins {
     uint16_t* sub_masks;     /* optional [D_cap]: rdg_blend_fwd stores, per sorted instance, the 16-bit mask of the
                               * 4x4-pixel sub-tiles the Gaussian can reach; rdg_blend_bwd reads it back (NULL:
                               * the backward pass recomputes it) */
+    uint32_t* tile_order;    /* optional [tiles]: rdg_bin_tiles writes the tile ids by descending list length; the blend
+                              * kernels then launch their CTAs in that order (longest tiles first).  NULL: row-major
+                              * order.  rdg_bin does not write it - pass NULL with that path. */
 } RdgBins;
 
 typedef struct RdgImage {

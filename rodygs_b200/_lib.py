@@ -43,7 +43,7 @@ class RdgGeom(C.Structure):
 
 class RdgBins(C.Structure):
     _fields_ = [("keys_sorted", c_ptr), ("vals_sorted", c_ptr), ("ranges", c_ptr), ("point_offsets", c_ptr),
-                ("num_rendered", c_ptr), ("keys_unsorted", c_ptr), ("vals_unsorted", c_ptr), ("sub_masks", c_ptr)]
+                ("num_rendered", c_ptr), ("keys_unsorted", c_ptr), ("vals_unsorted", c_ptr), ("sub_masks", c_ptr), ("tile_order", c_ptr)]
 
 
 class RdgImage(C.Structure):

@@ -219,9 +219,10 @@ __global__ void __launch_bounds__(BATCH, 6) blend_fwd_kernel(const uint2* __rest
                                                              int W, int H, int gx, float* __restrict__ out_color,
                                                              float* __restrict__ out_depth, float* __restrict__ out_alpha,
                                                              float* __restrict__ out_T, uint32_t* __restrict__ out_ncontrib,
-                                                             uint16_t* __restrict__ sub_masks) {
+                                                             uint16_t* __restrict__ sub_masks,
+                                                             const uint32_t* __restrict__ tile_order) {
     __shared__ Staged sm;
-    const int tile = blockIdx.x;
+    const int tile = tile_order ? (int)tile_order[blockIdx.x] : (int)blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = lane >> 3, l8 = lane & 7;
     const int sub = rdg_sub_of(warp, q);
@@ -462,12 +463,13 @@ __global__ void __launch_bounds__(BATCH, 6) blend_bwd_kernel(const uint2* __rest
                                                              const uint32_t* __restrict__ n_contrib,
                                                              const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
                                                              const float* __restrict__ dL_dalpha, float* __restrict__ acc,
-                                                             const uint16_t* __restrict__ sub_masks) {
+                                                             const uint16_t* __restrict__ sub_masks,
+                                                             const uint32_t* __restrict__ tile_order) {
     __shared__ Staged sm;
     __shared__ __align__(16) float pool[(POOL + 1) * PREC];       // + the scratch record of the null entry
     __shared__ uint32_t qlast[SUBS];
     __shared__ int wsum[NWARP];
-    const int tile = blockIdx.x;
+    const int tile = tile_order ? (int)tile_order[blockIdx.x] : (int)blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = lane >> 3, l8 = lane & 7;
     const int sub = rdg_sub_of(warp, q);
@@ -772,7 +774,7 @@ extern "C" int rdg_blend_fwd(int64_t n, const RdgGeom* geom, const RdgBins* bins
     kern<<<gx * gy, BATCH, 0, (cudaStream_t)stream>>>(
         (const uint2*)bins->ranges, bins->vals_sorted, (const float4*)geom->p0, (const float4*)geom->p1,
         (const float2*)geom->p2, view->bg, W, H, gx, out->color, out->depth, out->alpha, out->final_T, out->n_contrib,
-        bins->sub_masks);
+        bins->sub_masks, bins->tile_order);
     RDG_CHECK_LAUNCH();
     rdg_count_launches(1);
     return RDG_OK;
@@ -790,7 +792,7 @@ extern "C" int rdg_blend_bwd(int64_t n, const RdgGeom* geom, const RdgBins* bins
     kern<<<gx * gy, BATCH, 0, (cudaStream_t)stream>>>(
         (const uint2*)bins->ranges, bins->vals_sorted, (const float4*)geom->p0, (const float4*)geom->p1,
         (const float2*)geom->p2, view->bg, W, H, gx, fwd->final_T, fwd->n_contrib, dL_dcolor, dL_ddepth, dL_dalpha, acc,
-        bins->sub_masks);
+        bins->sub_masks, bins->tile_order);
     RDG_CHECK_LAUNCH();
     rdg_count_launches(1);
     return RDG_OK;

@@ -13,6 +13,7 @@ is in librodygs_b200.so; nothing in this file computes on the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Optional
 
@@ -44,6 +45,8 @@ class Config:
     #          emission-order arrays (point_offsets, unsorted keys/values) that the tests pin.
     binning: str = "tiles"
     emit_sorted_keys: bool = True       # write the sorted 64-bit keys (only verification reads them)
+    # launch the blend CTAs by descending tile list length (RdgBins.tile_order); RDG_TILE_ORDER=0 keeps row-major order (A/B)
+    tile_order: bool = os.environ.get("RDG_TILE_ORDER", "1") != "0"
 
 
 config = Config()
@@ -283,6 +286,8 @@ def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = T
         bins.keys_sorted, bins.vals_sorted = ptr(keys), ptr(vals)
         bins.ranges, bins.point_offsets, bins.num_rendered = ptr(ranges), ptr(point_offsets), ptr(num_rendered)
         bins.sub_masks = ptr(sub_masks)
+        tile_order = torch.empty(ntiles, dtype=torch.int32, device=dev) if (use_tiles and config.tile_order) else None
+        bins.tile_order = ptr(tile_order)
         if config.debug_keep_unsorted:
             extras["keys_unsorted"] = torch.empty(d_cap, dtype=torch.int64, device=dev)
             extras["vals_unsorted"] = torch.empty(d_cap, dtype=torch.int32, device=dev)
@@ -316,7 +321,7 @@ def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = T
     if stage_hook:
         stage_hook("blend_fwd")
 
-    extras.update({"keys_sorted": keys, "point_offsets": point_offsets, "sub_masks": sub_masks})
+    extras.update({"keys_sorted": keys, "point_offsets": point_offsets, "sub_masks": sub_masks, "tile_order": tile_order})
     state = FwdState(scene=scene, view=view, n=n, geom=geom, vals_sorted=vals, ranges=ranges,
                      num_rendered=num_rendered, final_T=final_T, n_contrib=n_contrib, d_cap=d_cap, extras=extras)
     return color, depth, alpha, geom["radii"], state
@@ -369,6 +374,7 @@ def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: Sce
     bins = RdgBins()
     bins.vals_sorted, bins.ranges, bins.num_rendered = ptr(state.vals_sorted), ptr(state.ranges), ptr(state.num_rendered)
     bins.sub_masks = ptr(state.extras.get("sub_masks"))
+    bins.tile_order = ptr(state.extras.get("tile_order"))
     img = RdgImage()
     img.final_T, img.n_contrib = ptr(state.final_T), ptr(state.n_contrib)
 

@@ -36,7 +36,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(_lib.RdgSet) == 6 * 8 + 2 * 4
     assert C.sizeof(_lib.RdgView) == 2 * 4 + 3 * 4 + 3 * 4 + 3 * 8
     assert C.sizeof(_lib.RdgGeom) == 8 * 8
-    assert C.sizeof(_lib.RdgBins) == 8 * 8
+    assert C.sizeof(_lib.RdgBins) == 9 * 8
     assert C.sizeof(_lib.RdgImage) == 5 * 8
     assert C.sizeof(_lib.RdgSetGrad) == 6 * 8
     assert C.sizeof(_lib.RdgSceneGrad) == 2 * 48 + 8 * 8
