@@ -159,6 +159,12 @@ int rdg_abi_version(void);
 const char* rdg_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
 uint64_t rdg_launch_count(void);
+/* A/B switches and test knobs of the launchers (process-wide; initial value from the environment variable RDG_<NAME>):
+ *   "pre_db"       1 (default): rdg_preprocess_fwd / _bwd double-buffer their SH staging; 0: single buffer
+ *   "pre_grid_cap" > 0: cap on the persistent grid of the two preprocess kernels (tests: forces many chunks per CTA)
+ *   "dtable_v1"    1: first version of the dL/dtable reduction
+ * Returns RDG_E_ARG for an unknown name. */
+int rdg_set_tunable(const char* name, int32_t value);
 
 /* ---- forward ------------------------------------------------------------ */
 

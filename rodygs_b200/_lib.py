@@ -93,6 +93,7 @@ SYMBOLS = {
     "rdg_abi_version": (C.c_int, []),
     "rdg_last_error": (C.c_char_p, []),
     "rdg_launch_count": (C.c_uint64, []),
+    "rdg_set_tunable": (C.c_int, [C.c_char_p, C.c_int32]),
     "rdg_alpha_reg": (C.c_int, [c_ptr, C.c_int64, C.c_float, c_ptr, c_ptr, c_ptr]),
     "rdg_preprocess_fwd": (C.c_int, [C.POINTER(RdgScene), C.POINTER(RdgView), C.POINTER(RdgGeom), c_ptr]),
     "rdg_bin_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
@@ -168,6 +169,11 @@ def load() -> C.CDLL:
         raise RuntimeError("librodygs_b200.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+def set_tunable(name: str, value: int) -> None:
+    """A/B switches / test knobs of the launchers (include/rodygs_b200.h: rdg_set_tunable)."""
+    check(load().rdg_set_tunable(name.encode(), int(value)))
 
 
 def check(rc: int) -> None:

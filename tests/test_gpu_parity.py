@@ -214,11 +214,31 @@ def test_known_answer_single_gaussian():
     assert radii.item() == math.ceil(3 * math.sqrt(var + math.sqrt(0.1)))
 
 
-def test_fused_dynamic_path_matches_oracle_chain():
+@pytest.fixture
+def _tunables():
+    from rodygs_b200 import _lib
+    yield _lib.set_tunable
+    for name, v in (("pre_db", 1), ("pre_grid_cap", 0), ("dtable_v1", 0)):
+        _lib.set_tunable(name, v)
+
+
+@pytest.mark.parametrize("n,cap,db,dt1", [(3000, 2, 1, 0), (2602, 3, 1, 0), (2602, 2, 0, 1), (3000, 0, 0, 1)])
+def test_fused_path_multi_chunk_staging(_tunables, n, cap, db, dt1):
+    """The persistent preprocess kernels with several chunks per CTA (grid capped), double-buffered and single-buffered
+    SH staging, chunks whose row count is not a multiple of 4 (2602 -> 1301 per model -> a 21-row last chunk that
+    cannot be bulk-copied, in the middle of a CTA's chunk sequence), and both dL/dtable reductions."""
+    _tunables("pre_grid_cap", cap)
+    _tunables("pre_db", db)
+    _tunables("dtable_v1", dt1)
+    test_fused_dynamic_path_matches_oracle_chain(n)
+    test_fused_path_bitexact_given_its_own_activations(n)
+
+
+def test_fused_dynamic_path_matches_oracle_chain(n=3000):
     """Raw parameters + deformation fused in the kernel vs the reference chain on the CPU
     (activations -> deformation -> concat -> rasterize), forward and all gradients."""
     from rodygs_b200.dynamic import GaussianParams, render_dynamic
-    H, W, n, T = 96, 128, 3000, 6
+    H, W, T = 96, 128, 6
     sc, cam = helpers.small_scene(n, H, W, T, seed=21)
     bg = torch.tensor([0.0, 0.0, 0.0])
     up = _upstream_grads(H, W)
@@ -268,10 +288,10 @@ def test_fused_dynamic_path_matches_oracle_chain():
         assert err <= GRAD_TOL, f"grad {name}: rel err {err:.3e}"
 
 
-def test_fused_path_bitexact_given_its_own_activations():
+def test_fused_path_bitexact_given_its_own_activations(n=2000):
     """The fused kernel's integer outputs are bit-exact w.r.t. the oracle evaluated on the
     activated values the kernel itself produced (isolates exp()/sigmoid ulp differences)."""
-    H, W, n, T = 64, 96, 2000, 5
+    H, W, T = 64, 96, 5
     sc, cam = helpers.small_scene(n, H, W, T, seed=33)
     engine.config.debug_activated = True
     dev = "cuda"
