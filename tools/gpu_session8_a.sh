@@ -48,9 +48,12 @@ for r in rows:
     if 'basis_mlp' in r['Kernel Name']: print('  %-50s %8.1f us'%(r['Kernel Name'][:50],us(r)))
 PY
 # 5. ncu --set full of the changed kernels
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"preprocess_fwd|preprocess_bwd|dtable2|basis_mlp|tile_scan" -s 8 -c 12 -o gpurun_out/prof_k -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_k.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"preprocess_fwd|preprocess_bwd|dtable2|tile_scan" -s 14 -c 4 -o gpurun_out/prof_k -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_k.log 2>&1
 echo "ncu exit $?"
 ncu -i gpurun_out/prof_k.ncu-rep --page raw --csv > gpurun_out/prof_k_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_k.ncu-rep --page details > gpurun_out/prof_k_details.txt 2>/dev/null
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"basis_mlp" -s 9 -c 3 -o gpurun_out/prof_mlp -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_mlp.log 2>&1
+echo "ncu mlp exit $?"
+ncu -i gpurun_out/prof_mlp.ncu-rep --page raw --csv > gpurun_out/prof_mlp_raw.csv 2>/dev/null
 sz=$(stat -c %s gpurun_out/prof_k.ncu-rep 2>/dev/null || echo 0); if [ "$sz" -gt 25000000 ]; then rm -f gpurun_out/prof_k.ncu-rep; echo "rep dropped ($sz bytes)"; fi
 ls -la gpurun_out/ | head -30
