@@ -13,16 +13,19 @@
 // B200 mapping.  68 656 parameters (275 KB) and at most a few hundred rows: the work (7 M FMA at T = 100) is three
 // orders of magnitude below anything that could load an SM, so this is a LATENCY problem, not a roofline one; the
 // parameters stay in L2 (126 MB) and every CTA streams them once.
-//   forward  : one CTA per row, the row's activations live in shared memory, one thread per output neuron
-//              (float4 row reads when the row is 16-byte aligned).
-//   backward : pass A, one CTA per row, back-propagates the row through the layers (transposed weight reads are
-//              the coalesced direction here) and stores the per-layer activations and pre-activation gradients;
+//   forward  : one CTA (8 warps) per row, the row's activations live in shared memory; a group of n_in/4 lanes owns
+//              one output neuron and reads its weight row with coalesced 16-byte loads, 8 row groups in flight per warp
+//              before the first shuffle (first version: one thread per neuron walking its row - 27 us, 4 % issue-active).
+//   backward : pass A, one CTA per row, back-propagates the row through the layers; the transposed products read the
+//              weights along the coalesced direction (4 columns per thread, the row range split over the thread groups,
+//              partial sums joined in shared memory; first version: one thread per column, 121 us) and the per-layer
+//              activations and pre-activation gradients are stored;
 //              pass B, one thread per PARAMETER, contracts those two [rows, .] panels over the rows - a fixed
 //              summation order instead of rows x 68 656 float atomics.
 #include <math.h>
 #include "common.cuh"
 
-#define MLP_BLOCK 128
+#define MLP_BLOCK 256
 #define MLP_MAX_WIDTH 256
 #define MLP_MAX_HEADS 2048   // num_basis * (width / 4)
 #define MLP_MAX_OUT 256      // num_basis * out_dim
@@ -74,22 +77,78 @@ __device__ __forceinline__ float act_d(float z) {
     return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z);
 }
 
-// bias + <row, x>, row in global memory (L2-resident parameters), x in shared memory.
-__device__ __forceinline__ float dot_row(const float* __restrict__ row, const float* x, int n, float acc) {
-    if (((reinterpret_cast<uintptr_t>(row) | (uintptr_t)n * 4u) & 15u) == 0) {
-        const float4* r4 = reinterpret_cast<const float4*>(row);
-        float a0 = acc, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        for (int i = 0; i < n / 4; ++i) {
-            const float4 w = __ldg(r4 + i);
-            a0 = fmaf(w.x, x[4 * i], a0);
-            a1 = fmaf(w.y, x[4 * i + 1], a1);
-            a2 = fmaf(w.z, x[4 * i + 2], a2);
-            a3 = fmaf(w.w, x[4 * i + 3], a3);
+// y[r] = act(bias[r] + <W[r, :], x>) for r < n_out; W row-major [n_out, n_in] in global memory (L2-resident), x in
+// shared memory.  Warp-cooperative: a group of G lanes owns one row and reads it with coalesced 16-byte loads (G =
+// n_in / 4 lanes, at most 32), 32 / G rows per warp instruction, UNROLL row-groups in flight per warp before the first
+// shuffle - the whole problem is load latency (3 warps per SM), so independent loads in flight are what matters.
+// Rows that are not 16-byte aligned (the 53-wide first layer) take the scalar variant: 32 lanes per row.
+// xblock > 0: block-diagonal layer - row r reads x + (r / xblock) * n_in (the second head layers: basis k has its own
+// hidden units); xblock = 0: every row reads the same x.
+template <int ACT, bool ACTIVATE>
+__device__ __forceinline__ void layer_rows(const float* __restrict__ Wm, const float* __restrict__ bias, const float* x,
+                                           int n_in, int n_out, float* y, float* z_out, int xblock = 0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = MLP_BLOCK / 32;
+    const bool vec = ((reinterpret_cast<uintptr_t>(Wm) & 15u) == 0) && (n_in % 4 == 0) && (n_in <= 128) &&
+                     ((n_in / 4) & (n_in / 4 - 1)) == 0;
+    if (vec) {
+        const int G = n_in / 4;                 // lanes per row (power of two, <= 32)
+        const int rpw = 32 / G;                 // rows per warp instruction
+        const int sub = lane / G, gl = lane - sub * G;
+        constexpr int UNROLL = 8;
+        for (int r0 = warp * rpw * UNROLL; r0 < n_out; r0 += nwarp * rpw * UNROLL) {
+            float acc[UNROLL];
+            float4 w[UNROLL];
+            float bz[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {        // rows past the end are clamped (loaded, never written): no branches
+                const int r = min(r0 + u * rpw + sub, n_out - 1);
+                w[u] = __ldg(reinterpret_cast<const float4*>(Wm + (size_t)r * n_in) + gl);
+                bz[u] = __ldg(bias + r);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int r = min(r0 + u * rpw + sub, n_out - 1);
+                const float4 xv = *reinterpret_cast<const float4*>(x + (xblock ? (r / xblock) * n_in : 0) + 4 * gl);
+                acc[u] = (w[u].x * xv.x + w[u].y * xv.y) + (w[u].z * xv.z + w[u].w * xv.w);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                float v = acc[u];
+                for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                const int r = r0 + u * rpw + sub;
+                if (gl == 0 && r < n_out) {
+                    const float z = v + bz[u];
+                    if (z_out) z_out[r] = z;
+                    y[r] = ACTIVATE ? act_f<ACT>(z) : z;
+                }
+            }
         }
-        return (a0 + a1) + (a2 + a3);
+    } else {
+        constexpr int UNROLL = 4;
+        for (int r0 = warp * UNROLL; r0 < n_out; r0 += nwarp * UNROLL) {
+            float acc[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int r = min(r0 + u, n_out - 1);
+                float a = lane == 0 ? __ldg(bias + r) : 0.f;      // the bias rides in lane 0's partial sum
+                const float* xr = x + (xblock ? (r / xblock) * n_in : 0);
+                for (int i = lane; i < n_in; i += 32) a = fmaf(__ldg(Wm + (size_t)r * n_in + i), xr[i], a);
+                acc[u] = a;
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                float v = acc[u];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                const int r = r0 + u;
+                if (lane == 0 && r < n_out) {
+                    const float z = v;
+                    if (z_out) z_out[r] = z;
+                    y[r] = ACTIVATE ? act_f<ACT>(z) : z;
+                }
+            }
+        }
     }
-    for (int i = 0; i < n; ++i) acc = fmaf(__ldg(row + i), x[i], acc);
-    return acc;
 }
 
 // One row of the batch: embedding (from `emb` or from `times` x `freqs_pi`) into x.
@@ -130,35 +189,74 @@ __global__ void __launch_bounds__(MLP_BLOCK) basis_mlp_fwd_kernel(MlpDims d, con
     load_embedding(d, m, emb, times, freqs_pi, x);
     __syncthreads();
     if (sv) for (int i = threadIdx.x; i < d.E; i += MLP_BLOCK) sv[d.sx + i] = x[i];
-    for (int j = threadIdx.x; j < d.W; j += MLP_BLOCK) {
-        const float z = dot_row(P + d.w1 + (size_t)j * d.E, x, d.E, P[d.b1 + j]);
-        if (sv) sv[d.s1 + j] = z;
-        a1[j] = act_f<ACT>(z);
-    }
+    layer_rows<ACT, true>(P + d.w1, P + d.b1, x, d.E, d.W, a1, sv ? sv + d.s1 : nullptr);
     __syncthreads();
-    for (int j = threadIdx.x; j < d.W; j += MLP_BLOCK) {
-        const float z = dot_row(P + d.w2 + (size_t)j * d.W, a1, d.W, P[d.b2 + j]);
-        if (sv) sv[d.s2 + j] = z;
-        a2[j] = act_f<ACT>(z);
-    }
+    layer_rows<ACT, true>(P + d.w2, P + d.b2, a1, d.W, d.W, a2, sv ? sv + d.s2 : nullptr);
     __syncthreads();
-    for (int j = threadIdx.x; j < d.H; j += MLP_BLOCK) {
-        const float z = dot_row(P + d.w3 + (size_t)j * d.W, a2, d.W, P[d.b3 + j]);
-        if (sv) sv[d.s3 + j] = z;
-        a3[j] = act_f<ACT>(z);
-    }
+    layer_rows<ACT, true>(P + d.w3, P + d.b3, a2, d.W, d.H, a3, sv ? sv + d.s3 : nullptr);
     __syncthreads();
-    for (int r = threadIdx.x; r < d.NQ; r += MLP_BLOCK) {      // r = basis k * Q + hidden unit
-        const float z = dot_row(P + d.h0 + (size_t)r * d.H, a3, d.H, P[d.hb0 + r]);
-        if (sv) sv[d.su + r] = z;
-        au[r] = act_f<ACT>(z);
-    }
+    // the num_basis first head layers share their input: one [nb*Q, H] matrix
+    layer_rows<ACT, true>(P + d.h0, P + d.hb0, a3, d.H, d.NQ, au, sv ? sv + d.su : nullptr);
     __syncthreads();
     // row 0 (the query time) may have its own destination, so that B(t) and the table land where the trainer keeps them
     float* out_row = basis_row0 ? (m == 0 ? basis_row0 : basis + (size_t)(m - 1) * d.NO) : basis + (size_t)m * d.NO;
-    for (int r = threadIdx.x; r < d.NO; r += MLP_BLOCK) {      // r = basis k * O + output
-        const int k = r / d.O;
-        out_row[r] = dot_row(P + d.h2 + (size_t)r * d.Q, au + k * d.Q, d.Q, P[d.hb2 + r]);
+    // second head layers: block-diagonal, basis k reads its own Q hidden units
+    layer_rows<ACT, false>(P + d.h2, P + d.hb2, au, d.Q, d.NO, out_row, nullptr, d.O);
+}
+
+// out[i] = act'(z[i]) * sum_j W[j, i] g[j]  (i < n_cols, j < n_rows): the transposed product of the backward pass.  The
+// columns are the coalesced direction; a thread owns 4 adjacent columns (16-byte loads) of every `parts`-th row, so the
+// j range is split over MLP_BLOCK / (n_cols / 4) thread groups and each thread has up to 8 independent loads in
+// flight; the partial sums meet in shared memory.  out_s (shared) and out_g (global, the dz panel) both receive it.
+template <int ACT>
+__device__ __forceinline__ void layer_cols(const float* __restrict__ Wm, const float* g, int n_rows, int n_cols,
+                                           const float* __restrict__ z, float* out_s, float* out_g, float4* scratch) {
+    const int c4n = n_cols / 4;
+    const bool vec = ((reinterpret_cast<uintptr_t>(Wm) & 15u) == 0) && (n_cols % 4 == 0) && c4n <= MLP_BLOCK && (MLP_BLOCK % c4n) == 0;
+    if (vec) {
+        const int parts = MLP_BLOCK / c4n, part = threadIdx.x / c4n, c4 = threadIdx.x - part * c4n;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* col = reinterpret_cast<const float4*>(Wm) + c4;
+        int j = part;
+        for (; j + 7 * parts < n_rows; j += 8 * parts) {      // 8 independent 16-byte loads in flight, then the FMAs
+            float4 w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) w[u] = __ldg(col + (size_t)(j + u * parts) * c4n);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float gj = g[j + u * parts];
+                acc.x = fmaf(w[u].x, gj, acc.x); acc.y = fmaf(w[u].y, gj, acc.y);
+                acc.z = fmaf(w[u].z, gj, acc.z); acc.w = fmaf(w[u].w, gj, acc.w);
+            }
+        }
+        for (; j < n_rows; j += parts) {
+            const float4 w = __ldg(col + (size_t)j * c4n);
+            const float gj = g[j];
+            acc.x = fmaf(w.x, gj, acc.x); acc.y = fmaf(w.y, gj, acc.y); acc.z = fmaf(w.z, gj, acc.z); acc.w = fmaf(w.w, gj, acc.w);
+        }
+        scratch[threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.x < c4n) {
+            float4 t = scratch[threadIdx.x];
+            for (int q = 1; q < parts; ++q) {
+                const float4 u = scratch[q * c4n + threadIdx.x];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            const int i = 4 * threadIdx.x;
+            t.x *= act_d<ACT>(z[i]); t.y *= act_d<ACT>(z[i + 1]); t.z *= act_d<ACT>(z[i + 2]); t.w *= act_d<ACT>(z[i + 3]);
+            out_s[i] = t.x; out_s[i + 1] = t.y; out_s[i + 2] = t.z; out_s[i + 3] = t.w;
+            out_g[i] = t.x; out_g[i + 1] = t.y; out_g[i + 2] = t.z; out_g[i + 3] = t.w;
+        }
+        __syncthreads();
+    } else {
+        for (int i = threadIdx.x; i < n_cols; i += MLP_BLOCK) {
+            float a = 0.f;
+            for (int j = 0; j < n_rows; ++j) a = fmaf(__ldg(Wm + (size_t)j * n_cols + i), g[j], a);
+            a *= act_d<ACT>(z[i]);
+            out_s[i] = a;
+            out_g[i] = a;
+        }
+        __syncthreads();
     }
 }
 
@@ -173,9 +271,9 @@ __global__ void __launch_bounds__(MLP_BLOCK) basis_mlp_bwd_rows_kernel(MlpDims d
                                                                        float* __restrict__ ws_dz) {
     __shared__ float g_out[MLP_MAX_OUT];
     __shared__ float du[MLP_MAX_HEADS];
-    __shared__ float dzs[MLP_MAX_WIDTH];     // dz of the layer being propagated
-    __shared__ float dzn[MLP_MAX_WIDTH];
-    __shared__ float part[MLP_BLOCK];
+    __shared__ float dz_a[MLP_MAX_WIDTH];
+    __shared__ float dz_b[MLP_MAX_WIDTH];
+    __shared__ __align__(16) float4 scratch[MLP_BLOCK];
     const int m = blockIdx.x;
     const float* sv = saved + (size_t)m * d.S;
     float* act = ws_act + (size_t)m * d.S;
@@ -187,7 +285,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) basis_mlp_bwd_rows_kernel(MlpDims d
     for (int i = threadIdx.x; i < d.E; i += MLP_BLOCK) act[d.sx + i] = sv[d.sx + i];
     for (int i = threadIdx.x; i < d.S - d.E; i += MLP_BLOCK) act[d.s1 + i] = act_f<ACT>(sv[d.s1 + i]);
     __syncthreads();
-    // heads, second linear: da_u[k,i] = sum_o H2[k,o,i] dB[k,o]   (coalesced over i)
+    // heads, second linear (block-diagonal, 7 terms): du[k,i] = act'(u[k,i]) * sum_o H2[k,o,i] dB[k,o]   (coalesced over i)
     for (int r = threadIdx.x; r < d.NQ; r += MLP_BLOCK) {
         const int k = r / d.Q, i = r - k * d.Q;
         float s = 0.f;
@@ -197,41 +295,12 @@ __global__ void __launch_bounds__(MLP_BLOCK) basis_mlp_bwd_rows_kernel(MlpDims d
         dz[d.su + r] = g;
     }
     __syncthreads();
-    // heads, first linear: da3[j] = sum_r H0[r, j] du[r]   (coalesced over j; the r range is split over MLP_BLOCK/H groups)
-    {
-        const int groups = d.H <= MLP_BLOCK ? MLP_BLOCK / d.H : 1;
-        for (int j0 = 0; j0 < d.H; j0 += MLP_BLOCK) {
-            const int j = j0 + (groups > 1 ? threadIdx.x % d.H : threadIdx.x);
-            const int grp = groups > 1 ? threadIdx.x / d.H : 0;
-            float s = 0.f;
-            if (j < d.H && grp < groups)
-                for (int r = grp; r < d.NQ; r += groups) s = fmaf(__ldg(P + d.h0 + (size_t)r * d.H + j), du[r], s);
-            part[threadIdx.x] = s;
-            __syncthreads();
-            if (grp == 0 && j < d.H) {
-                for (int g2 = 1; g2 < groups; ++g2) s += part[g2 * d.H + j];
-                const float g = s * act_d<ACT>(sv[d.s3 + j]);
-                dzs[j] = g;
-                dz[d.s3 + j] = g;
-            }
-            __syncthreads();
-        }
-    }
-    // timenet layer 3 -> 2: da2[i] = sum_j W3[j, i] dz3[j]
-    for (int i = threadIdx.x; i < d.W; i += MLP_BLOCK) {
-        float s = 0.f;
-        for (int j = 0; j < d.H; ++j) s = fmaf(__ldg(P + d.w3 + (size_t)j * d.W + i), dzs[j], s);
-        const float g = s * act_d<ACT>(sv[d.s2 + i]);
-        dzn[i] = g;
-        dz[d.s2 + i] = g;
-    }
-    __syncthreads();
-    // layer 2 -> 1: da1[i] = sum_j W2[j, i] dz2[j]
-    for (int i = threadIdx.x; i < d.W; i += MLP_BLOCK) {
-        float s = 0.f;
-        for (int j = 0; j < d.W; ++j) s = fmaf(__ldg(P + d.w2 + (size_t)j * d.W + i), dzn[j], s);
-        dz[d.s1 + i] = s * act_d<ACT>(sv[d.s1 + i]);
-    }
+    // heads, first linear: dz3[j] = act'(z3[j]) * sum_r H0[r, j] du[r]
+    layer_cols<ACT>(P + d.h0, du, d.NQ, d.H, sv + d.s3, dz_a, dz + d.s3, scratch);
+    // timenet 3 -> 2: dz2[i] = act'(z2[i]) * sum_j W3[j, i] dz3[j]
+    layer_cols<ACT>(P + d.w3, dz_a, d.H, d.W, sv + d.s2, dz_b, dz + d.s2, scratch);
+    // timenet 2 -> 1: dz1[i] = act'(z1[i]) * sum_j W2[j, i] dz2[j]
+    layer_cols<ACT>(P + d.w2, dz_b, d.W, d.W, sv + d.s1, dz_a, dz + d.s1, scratch);
 }
 
 // Backward pass B: one thread per parameter; grad[p] (+)= sum_m dz[m, out(p)] * act[m, in(p)].
@@ -305,10 +374,10 @@ extern "C" int64_t rdg_basis_mlp_bwd_workspace_bytes(int32_t rows, int32_t emb_d
 extern "C" int rdg_basis_mlp_fwd(const RdgBasisMlp* a, void* stream) {
     MlpDims d;
     if (int rc = check_dims(a, &d)) return rc;
+    if (a->rows == 0) return RDG_OK;
     RDG_CHECK_ARG(a->params && (a->basis || (a->basis_row0 && a->rows <= 1)), "params / basis must not be NULL");
     RDG_CHECK_ARG(a->emb || (a->times && a->freqs_pi), "give emb, or times and freqs_pi");
     RDG_CHECK_ARG(a->emb || a->emb_dim % 2 == 1, "computed embedding needs emb_dim = 2 * multires + 1");
-    if (a->rows == 0) return RDG_OK;
     cudaStream_t s = (cudaStream_t)stream;
     if (a->activation == 0)
         basis_mlp_fwd_kernel<0><<<a->rows, MLP_BLOCK, 0, s>>>(d, a->params, a->emb, a->times, a->freqs_pi, a->basis, a->basis_row0,

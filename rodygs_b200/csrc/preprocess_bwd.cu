@@ -57,21 +57,21 @@ __device__ __forceinline__ void sh_basis_grad(float x, float y, float z, float* 
     }
 }
 
-// DB = two row buffers (default; RDG_PRE_DB=0 selects the single-buffer kernel for A/B): the NEXT chunk's SH rows are
-// requested at the top of the current chunk, so a bulk load is in flight during the whole per-Gaussian chain rule and the
-// write-out instead of only during the geometry fetch (ncu r01, single buffer: 39 % of DRAM peak, long-scoreboard stalls).
-template <bool RAW, int DEG, bool DB>
-__global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreBwdParams p) {
+// MINB: CTAs per SM the register allocation must allow (2: 128 registers, the default; 3: 80 registers, A/B through the
+// "pre_bwd_minb" tunable).  Like the forward kernel this one is latency bound (ncu r01: 39 % of DRAM peak, long-scoreboard
+// stalls); double-buffering its SH rows was measured and did not help (0.489 vs 0.464 ms, profiles/r01_ab_v12_*.json).
+template <bool RAW, int DEG, int MINB>
+__global__ void __launch_bounds__(RDG_BLOCK, MINB) preprocess_bwd_kernel(const PreBwdParams p) {
     extern __shared__ __align__(128) float smem[];
     constexpr int K = (DEG + 1) * (DEG + 1);
     constexpr int NREST = 3 * (K - 1);
     const RdgScene& sc = p.sc;
     const bool use_sh = sc.colors_precomp == nullptr;
     const bool deform = RAW && sc.use_deform && sc.n_dynamic > 0;
-    // [256][SH_ROW] row buffer(s): in SH rest coefficients, out their gradients; then [16*7] B(t)
-    float* bt_s = smem + (DB ? 2 : 1) * RDG_BLOCK * SH_ROW;
+    float* sh_s = smem;                       // [256][SH_ROW] in: SH rest coefficients, out: their gradients
+    float* bt_s = smem + RDG_BLOCK * SH_ROW;  // [16*7] B(t)
     __shared__ float red_s[RDG_BLOCK / 32][16];
-    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ __align__(8) uint64_t bar;
 
     RdgCam cam;
     rdg_load_cam(cam, p.view.viewmatrix, p.view.projmatrix, p.view.tanfovx, p.view.tanfovy, p.view.width, p.view.height);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
 
     if (deform)
         for (int e = threadIdx.x; e < sc.num_basis * 7; e += RDG_BLOCK) bt_s[e] = sc.basis_t[e];
-    if (threadIdx.x == 0) { rdg_mbar_init(&bars[0], 1); rdg_mbar_init(&bars[1], 1); }
+    if (threadIdx.x == 0) rdg_mbar_init(&bar, 1);
     __syncthreads();
 
     float poseV[12];   // dL/dV rows 0..2 (row-major), this thread's partial sum
@@ -92,35 +92,9 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
 
     const int lane = threadIdx.x & 31;
     const int64_t cs = (sc.n_static + RDG_BLOCK - 1) / RDG_BLOCK, cd = (sc.n_dynamic + RDG_BLOCK - 1) / RDG_BLOCK;
-    // chunk -> source of its SH rows when they can come in by one bulk copy, else nullptr
-    auto bulk_src = [&](int64_t chunk, int& cnt_out) -> const float* {
-        const bool dyn_c = chunk >= cs;
-        const RdgSet& set_c = dyn_c ? sc.dy : sc.st;
-        const int64_t lb = (dyn_c ? chunk - cs : chunk) * RDG_BLOCK;
-        const int c = (int)min((int64_t)RDG_BLOCK, (dyn_c ? sc.n_dynamic : sc.n_static) - lb);
-        cnt_out = c;
-        const bool ok = use_sh && NREST == SH_ROW && set_c.sh_rest_stride == SH_ROW && p.use_tma && (c & 3) == 0;
-        return ok ? set_c.sh_rest + lb * SH_ROW : nullptr;
-    };
-    uint32_t phase = 0;          // bit b: parity of the next completion of bars[b]
-    bool prefetched = false;     // the current chunk's bulk load was issued during the previous iteration
-    if (DB && (int64_t)blockIdx.x < cs + cd) {
-        int c0;
-        const float* src0 = bulk_src(blockIdx.x, c0);
-        if (src0) {
-            if (threadIdx.x == 0) {
-                rdg_fence_proxy_async();
-                rdg_bulk_load(smem, src0, (uint32_t)(c0 * SH_ROW * sizeof(float)), &bars[0]);
-            }
-            prefetched = true;
-        }
-    }
+    uint32_t phase = 0;
     bool store_pending = false;
-    int it = 0;
-    for (int64_t chunk = blockIdx.x; chunk < cs + cd; chunk += gridDim.x, ++it) {
-        const int b = DB ? (it & 1) : 0;
-        float* sh_s = smem + b * RDG_BLOCK * SH_ROW;
-        uint64_t& bar = bars[b];
+    for (int64_t chunk = blockIdx.x; chunk < cs + cd; chunk += gridDim.x) {
         const bool dyn = chunk >= cs;
         const RdgSet& set = dyn ? sc.dy : sc.st;
         const RdgSetGrad& gs = dyn ? p.gr.dy : p.gr.st;
@@ -139,21 +113,9 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
         const bool tma_out = full_rows && p.use_tma && gs.sh_rest != nullptr && (cnt & 3) == 0;
         if (threadIdx.x == 0 && store_pending) { rdg_bulk_store_wait_read(); store_pending = false; }
         __syncthreads();   // previous chunk fully written out / read
-        bool next_prefetched = false;
         if (use_sh && NREST > 0) {
-            if (DB && chunk + gridDim.x < cs + cd) {      // the other buffer is free: its store was waited for above
-                int cn;
-                const float* srcn = bulk_src(chunk + gridDim.x, cn);
-                if (srcn) {
-                    if (threadIdx.x == 0) {
-                        rdg_fence_proxy_async();
-                        rdg_bulk_load(smem + (b ^ 1) * RDG_BLOCK * SH_ROW, srcn, (uint32_t)(cn * SH_ROW * sizeof(float)), &bars[b ^ 1]);
-                    }
-                    next_prefetched = true;
-                }
-            }
             if (tma_in) {
-                if (!prefetched && threadIdx.x == 0) {
+                if (threadIdx.x == 0) {
                     rdg_fence_proxy_async();
                     rdg_bulk_load(sh_s, set.sh_rest + lbase * SH_ROW, (uint32_t)(cnt * SH_ROW * sizeof(float)), &bar);
                 }
@@ -272,10 +234,9 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
 
         // ---- colour: needs the staged SH rows ----
         if (use_sh && NREST > 0) {
-            if (tma_in) { rdg_mbar_wait(&bar, (phase >> b) & 1u); phase ^= 1u << b; }
+            if (tma_in) { rdg_mbar_wait(&bar, phase & 1u); ++phase; }
             else __syncthreads();
         }
-        prefetched = next_prefetched;
         if (vis) {
             if (use_sh) {
                 const unsigned cl = p.geom.clamped[i];
@@ -589,13 +550,12 @@ template <bool RAW, int DEG>
 static int launch_bwd(const PreBwdParams& p, int grid, size_t smem, cudaStream_t s) {
     const int cap = rdg_tunable(RDG_TUN_PRE_GRID_CAP);
     if (cap > 0 && grid > cap) grid = cap;
-    if (rdg_tunable(RDG_TUN_PRE_DB) != 0 && DEG == 3) {
-        const size_t smem2 = smem + (size_t)RDG_BLOCK * SH_ROW * sizeof(float);
-        RDG_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<RAW, DEG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        preprocess_bwd_kernel<RAW, DEG, true><<<grid, RDG_BLOCK, smem2, s>>>(p);
+    if (rdg_tunable(RDG_TUN_PRE_BWD_MINB) == 3) {
+        RDG_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<RAW, DEG, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        preprocess_bwd_kernel<RAW, DEG, 3><<<grid, RDG_BLOCK, smem, s>>>(p);
     } else {
-        RDG_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<RAW, DEG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        preprocess_bwd_kernel<RAW, DEG, false><<<grid, RDG_BLOCK, smem, s>>>(p);
+        RDG_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<RAW, DEG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        preprocess_bwd_kernel<RAW, DEG, 2><<<grid, RDG_BLOCK, smem, s>>>(p);
     }
     RDG_CHECK_LAUNCH();
     return RDG_OK;

@@ -16,7 +16,6 @@
 // 16-byte aligned 46 KB span: it is fetched by ONE cp.async.bulk (TMA) into shared memory
 // while the threads load their 44 B of geometry and run the projection; each thread then
 // reads its own row (stride 45 words: conflict-free).  46 KB per CTA -> 4 CTAs per SM.
-#include <stdlib.h>
 #include "scene.cuh"
 #include "tma.cuh"
 
@@ -29,19 +28,20 @@ struct PreFwdParams {
     int use_tma;
 };
 
-// DB = double-buffered SH staging (default; RDG_PRE_DB=0 selects the single-buffer kernel for A/B).  ncu r01 on the
-// single-buffer kernel: 36 % of DRAM peak, 2 CTAs per SM (86 registers), long-scoreboard stalls - the bulk load of a
-// chunk is only in flight while that chunk's own geometry is fetched, nothing is in flight while the SH sum and the
-// stores run.  With two 46 KB buffers the NEXT chunk's rows are requested before the current chunk is touched, so
-// every CTA keeps >= 46 KB in flight all the time (2 CTAs x 92 KB of shared memory per SM).
-template <bool RAW, int DEG, bool DB>
-__global__ void __launch_bounds__(RDG_BLOCK, DB ? 2 : 0) preprocess_fwd_kernel(const PreFwdParams p) {
+// MINB = CTAs per SM the register allocation must allow.  0: compiler's choice (86 registers -> 2 CTAs, 16 warps per SM);
+// 3: <= 80 registers -> 3 CTAs, 24 warps per SM.  ncu r01: the kernel is latency bound (long-scoreboard stalls on the
+// per-Gaussian fetch chain, 31 % issue-active, 36 % of DRAM peak), so resident warps are what it needs.  Double-buffering
+// the SH rows instead (two 46 KB buffers, next chunk's bulk load issued one chunk ahead) was measured and did NOT help
+// (0.266 vs 0.258 ms, profiles/r01_ab_v12_*.json): the bulk copy is not what the warps wait for.
+template <bool RAW, int DEG, int MINB>
+__global__ void __launch_bounds__(RDG_BLOCK, MINB) preprocess_fwd_kernel(const PreFwdParams p) {
     extern __shared__ __align__(128) float smem[];
     constexpr int K = (DEG + 1) * (DEG + 1);
     constexpr int NREST = 3 * (K - 1);
     const RdgScene& sc = p.sc;
-    float* bt_s = smem + (DB ? 2 : 1) * RDG_BLOCK * SH_ROW;  // [16*7] B(t), after the [256][SH_ROW] row buffer(s)
-    __shared__ __align__(8) uint64_t bars[2];
+    float* sh_s = smem;                       // [256][SH_ROW]
+    float* bt_s = smem + RDG_BLOCK * SH_ROW;  // [16*7] B(t)
+    __shared__ __align__(8) uint64_t bar;
 
     RdgCam cam;
     rdg_load_cam(cam, p.view.viewmatrix, p.view.projmatrix, p.view.tanfovx, p.view.tanfovy,
@@ -52,64 +52,26 @@ __global__ void __launch_bounds__(RDG_BLOCK, DB ? 2 : 0) preprocess_fwd_kernel(c
     const bool deform = RAW && sc.use_deform && sc.n_dynamic > 0;
     if (deform)
         for (int e = threadIdx.x; e < sc.num_basis * 7; e += RDG_BLOCK) bt_s[e] = sc.basis_t[e];
-    if (threadIdx.x == 0) { rdg_mbar_init(&bars[0], 1); rdg_mbar_init(&bars[1], 1); }
+    if (threadIdx.x == 0) rdg_mbar_init(&bar, 1);
     __syncthreads();
 
     const bool use_sh = (sc.colors_precomp == nullptr) && NREST > 0;
     const int64_t cs = (sc.n_static + RDG_BLOCK - 1) / RDG_BLOCK, cd = (sc.n_dynamic + RDG_BLOCK - 1) / RDG_BLOCK;
-    // chunk -> (rows source, row count) when its rows can come in by one bulk copy, else nullptr
-    auto bulk_src = [&](int64_t chunk, int& cnt_out) -> const float* {
-        const bool dyn_c = chunk >= cs;
-        const RdgSet& set_c = dyn_c ? sc.dy : sc.st;
-        const int64_t lb = (dyn_c ? chunk - cs : chunk) * RDG_BLOCK;
-        const int c = (int)min((int64_t)RDG_BLOCK, (dyn_c ? sc.n_dynamic : sc.n_static) - lb);
-        cnt_out = c;
-        const bool ok = use_sh && p.use_tma && NREST == SH_ROW && set_c.sh_rest_stride == SH_ROW && (c & 3) == 0;
-        return ok ? set_c.sh_rest + lb * SH_ROW : nullptr;
-    };
-    uint32_t phase = 0;          // bit b: parity of the next completion of bars[b]
-    bool prefetched = false;     // the current chunk's bulk load was issued during the previous iteration
-    if (DB && (int64_t)blockIdx.x < cs + cd) {
-        int c0;
-        const float* src0 = bulk_src(blockIdx.x, c0);
-        if (src0) {
-            if (threadIdx.x == 0) {
-                rdg_fence_proxy_async();
-                rdg_bulk_load(smem, src0, (uint32_t)(c0 * SH_ROW * sizeof(float)), &bars[0]);
-            }
-            prefetched = true;
-        }
-    }
-    int it = 0;
-    for (int64_t chunk = blockIdx.x; chunk < cs + cd; chunk += gridDim.x, ++it) {
+    uint32_t phase = 0;
+    for (int64_t chunk = blockIdx.x; chunk < cs + cd; chunk += gridDim.x) {
         const bool dyn = chunk >= cs;
         const RdgSet& set = dyn ? sc.dy : sc.st;
         const int64_t lbase = (dyn ? chunk - cs : chunk) * RDG_BLOCK;
         const int64_t n_set = dyn ? sc.n_dynamic : sc.n_static;
         const int cnt = (int)min((int64_t)RDG_BLOCK, n_set - lbase);
-        const int b = DB ? (it & 1) : 0;
-        float* sh_s = smem + b * RDG_BLOCK * SH_ROW;
-        uint64_t& bar = bars[b];
 
         // ---- stage this chunk's higher-order SH rows in shared memory ----
         bool tma = false;
-        bool next_prefetched = false;
         if (use_sh) {
-            __syncthreads();  // the previous chunk's readers are done with their buffer
-            if (DB && chunk + gridDim.x < cs + cd) {
-                int cn;
-                const float* srcn = bulk_src(chunk + gridDim.x, cn);
-                if (srcn) {
-                    if (threadIdx.x == 0) {
-                        rdg_fence_proxy_async();
-                        rdg_bulk_load(smem + (b ^ 1) * RDG_BLOCK * SH_ROW, srcn, (uint32_t)(cn * SH_ROW * sizeof(float)), &bars[b ^ 1]);
-                    }
-                    next_prefetched = true;
-                }
-            }
+            __syncthreads();  // previous chunk's readers are done with sh_s
             tma = p.use_tma && NREST == SH_ROW && set.sh_rest_stride == SH_ROW && (cnt & 3) == 0;
             if (tma) {
-                if (!prefetched && threadIdx.x == 0) {
+                if (threadIdx.x == 0) {
                     rdg_fence_proxy_async();
                     rdg_bulk_load(sh_s, set.sh_rest + lbase * SH_ROW, (uint32_t)(cnt * SH_ROW * sizeof(float)), &bar);
                 }
@@ -168,11 +130,10 @@ __global__ void __launch_bounds__(RDG_BLOCK, DB ? 2 : 0) preprocess_fwd_kernel(c
             }
         }
         if (use_sh) {
-            if (tma) rdg_mbar_wait(&bar, (phase >> b) & 1u);
+            if (tma) rdg_mbar_wait(&bar, phase & 1u);
             else __syncthreads();
         }
-        if (tma) phase ^= 1u << b;
-        prefetched = next_prefetched;
+        if (tma) ++phase;
         if (vis) {
             float rgb[3];
             unsigned clamped = 0;
@@ -217,14 +178,12 @@ template <bool RAW, int DEG>
 static int launch_fwd(const PreFwdParams& p, int grid, size_t smem, cudaStream_t s) {
     const int cap = rdg_tunable(RDG_TUN_PRE_GRID_CAP);
     if (cap > 0 && grid > cap) grid = cap;
-    if (rdg_tunable(RDG_TUN_PRE_DB) != 0 && DEG == 3) {     // lower degrees stage 0 / 9 / 24 floats per row: nothing to hide
-        const size_t smem2 = smem + (size_t)RDG_BLOCK * SH_ROW * sizeof(float);
-        const int grid2 = grid < RDG_SM_COUNT * 2 ? grid : RDG_SM_COUNT * 2;
-        RDG_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<RAW, DEG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        preprocess_fwd_kernel<RAW, DEG, true><<<grid2, RDG_BLOCK, smem2, s>>>(p);
+    if (rdg_tunable(RDG_TUN_PRE_FWD_MINB) == 3) {
+        RDG_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<RAW, DEG, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        preprocess_fwd_kernel<RAW, DEG, 3><<<grid, RDG_BLOCK, smem, s>>>(p);
     } else {
-        RDG_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<RAW, DEG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        preprocess_fwd_kernel<RAW, DEG, false><<<grid, RDG_BLOCK, smem, s>>>(p);
+        RDG_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<RAW, DEG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        preprocess_fwd_kernel<RAW, DEG, 0><<<grid, RDG_BLOCK, smem, s>>>(p);
     }
     RDG_CHECK_LAUNCH();
     return RDG_OK;

@@ -45,8 +45,10 @@ class Config:
     #          emission-order arrays (point_offsets, unsorted keys/values) that the tests pin.
     binning: str = "tiles"
     emit_sorted_keys: bool = True       # write the sorted 64-bit keys (only verification reads them)
-    # launch the blend CTAs by descending tile list length (RdgBins.tile_order); RDG_TILE_ORDER=0 keeps row-major order (A/B)
-    tile_order: bool = os.environ.get("RDG_TILE_ORDER", "1") != "0"
+    # launch the blend CTAs by descending tile list length (RdgBins.tile_order).  Off by default: measured on B200 at C4 the
+    # longest-first order is 2 % SLOWER in blend_bwd (1.282 vs 1.253 ms, profiles/r01_ab_v12_*.json) - row-major neighbours
+    # share Gaussians in L2, and that is worth more than a shorter last wave.  RDG_TILE_ORDER=1 turns it on.
+    tile_order: bool = os.environ.get("RDG_TILE_ORDER", "0") == "1"
 
 
 config = Config()

@@ -16,7 +16,7 @@ def _reset():
     engine.config.sync_free = False
     engine.config.debug_keep_unsorted = False
     engine.config.binning = "tiles"
-    engine.config.tile_order = True
+    engine.config.tile_order = False
 
 
 def _step(cfg, n_override=None):
@@ -38,6 +38,7 @@ def _forward(step, cam):
 @pytest.mark.parametrize("cfg,binning", [("c2_kubric", "tiles"), ("c2_kubric", "lsd"), ("c4_iphone", "tiles"), ("c4_iphone", "lsd")])
 def test_binning_tables_are_consistent_at_full_size(cfg, binning):
     engine.config.binning = binning
+    engine.config.tile_order = True      # optional longest-first launch order of the blend CTAs (off by default)
     step, cam, (N, H, W, T) = _step(cfg)
     (color, depth, alpha, radii), st = _forward(step, cam)
     D = int(st.num_rendered[0])
