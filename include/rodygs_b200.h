@@ -160,8 +160,6 @@ const char* rdg_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
 uint64_t rdg_launch_count(void);
 /* A/B switches and test knobs of the launchers (process-wide; initial value from the environment variable RDG_<NAME>):
- *   "pre_fwd_minb" 0 (default) / 3: CTAs per SM the register allocation of the rdg_preprocess_fwd kernel is built for
- *   "pre_bwd_minb" 2 (default) / 3: same for rdg_preprocess_bwd
  *   "pre_grid_cap" > 0: cap on the persistent grid of the two preprocess kernels (tests: forces many chunks per CTA)
  *   "dtable_v1"    1: first version of the dL/dtable reduction
  * Returns RDG_E_ARG for an unknown name. */

@@ -77,24 +77,25 @@ __device__ __forceinline__ float act_d(float z) {
     return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z);
 }
 
-// y[r] = act(bias[r] + <W[r, :], x>) for r < n_out; W row-major [n_out, n_in] in global memory (L2-resident), x in
-// shared memory.  Warp-cooperative: a group of G lanes owns one row and reads it with coalesced 16-byte loads (G =
-// n_in / 4 lanes, at most 32), 32 / G rows per warp instruction, UNROLL row-groups in flight per warp before the first
-// shuffle - the whole problem is load latency (3 warps per SM), so independent loads in flight are what matters.
-// Rows that are not 16-byte aligned (the 53-wide first layer) take the scalar variant: 32 lanes per row.
-// xblock > 0: block-diagonal layer - row r reads x + (r / xblock) * n_in (the second head layers: basis k has its own
-// hidden units); xblock = 0: every row reads the same x.
-template <int ACT, bool ACTIVATE>
+// y[r] = bias[r] + <W[r, :], x> for r < n_out; W row-major [n_out, n_in] in global memory (L2-resident), x in shared
+// memory.  Warp-cooperative: a group of G lanes owns one row and reads it with coalesced 16-byte loads (G = n_in / 4
+// lanes, at most 32), 32 / G rows per warp instruction, UNROLL row-groups in flight per warp before the first shuffle -
+// the whole problem is load latency (a few warps per SM), so independent loads in flight are what matters.  Rows that
+// are not 16-byte aligned (the 53-wide first layer) take the scalar variant: 32 lanes per row.  The activation is NOT
+// applied here (one lane per row would run erff divergently): the caller does it densely afterwards.
+// BLOCKED: block-diagonal layer - row r reads x + (r / xblock) * n_in (the second head layers: basis k has its own
+// hidden units); otherwise every row reads the same x.
+template <bool BLOCKED>
 __device__ __forceinline__ void layer_rows(const float* __restrict__ Wm, const float* __restrict__ bias, const float* x,
-                                           int n_in, int n_out, float* y, float* z_out, int xblock = 0) {
+                                           int n_in, int n_out, float* y, int xblock) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = MLP_BLOCK / 32;
     const bool vec = ((reinterpret_cast<uintptr_t>(Wm) & 15u) == 0) && (n_in % 4 == 0) && (n_in <= 128) &&
                      ((n_in / 4) & (n_in / 4 - 1)) == 0;
+    constexpr int UNROLL = 4;
     if (vec) {
         const int G = n_in / 4;                 // lanes per row (power of two, <= 32)
         const int rpw = 32 / G;                 // rows per warp instruction
         const int sub = lane / G, gl = lane - sub * G;
-        constexpr int UNROLL = 8;
         for (int r0 = warp * rpw * UNROLL; r0 < n_out; r0 += nwarp * rpw * UNROLL) {
             float acc[UNROLL];
             float4 w[UNROLL];
@@ -108,7 +109,7 @@ __device__ __forceinline__ void layer_rows(const float* __restrict__ Wm, const f
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const int r = min(r0 + u * rpw + sub, n_out - 1);
-                const float4 xv = *reinterpret_cast<const float4*>(x + (xblock ? (r / xblock) * n_in : 0) + 4 * gl);
+                const float4 xv = *reinterpret_cast<const float4*>(x + (BLOCKED ? (r / xblock) * n_in : 0) + 4 * gl);
                 acc[u] = (w[u].x * xv.x + w[u].y * xv.y) + (w[u].z * xv.z + w[u].w * xv.w);
             }
 #pragma unroll
@@ -116,22 +117,17 @@ __device__ __forceinline__ void layer_rows(const float* __restrict__ Wm, const f
                 float v = acc[u];
                 for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 const int r = r0 + u * rpw + sub;
-                if (gl == 0 && r < n_out) {
-                    const float z = v + bz[u];
-                    if (z_out) z_out[r] = z;
-                    y[r] = ACTIVATE ? act_f<ACT>(z) : z;
-                }
+                if (gl == 0 && r < n_out) y[r] = v + bz[u];
             }
         }
     } else {
-        constexpr int UNROLL = 4;
         for (int r0 = warp * UNROLL; r0 < n_out; r0 += nwarp * UNROLL) {
             float acc[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const int r = min(r0 + u, n_out - 1);
                 float a = lane == 0 ? __ldg(bias + r) : 0.f;      // the bias rides in lane 0's partial sum
-                const float* xr = x + (xblock ? (r / xblock) * n_in : 0);
+                const float* xr = x + (BLOCKED ? (r / xblock) * n_in : 0);
                 for (int i = lane; i < n_in; i += 32) a = fmaf(__ldg(Wm + (size_t)r * n_in + i), xr[i], a);
                 acc[u] = a;
             }
@@ -141,14 +137,22 @@ __device__ __forceinline__ void layer_rows(const float* __restrict__ Wm, const f
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 const int r = r0 + u;
-                if (lane == 0 && r < n_out) {
-                    const float z = v;
-                    if (z_out) z_out[r] = z;
-                    y[r] = ACTIVATE ? act_f<ACT>(z) : z;
-                }
+                if (lane == 0 && r < n_out) y[r] = v;
             }
         }
     }
+}
+
+// y <- act(y) in place (shared memory), the pre-activation kept in z_out (global, may be NULL).  Ends with a barrier.
+template <int ACT>
+__device__ __forceinline__ void activate(float* y, int n, float* z_out) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += MLP_BLOCK) {
+        const float z = y[i];
+        if (z_out) z_out[i] = z;
+        y[i] = act_f<ACT>(z);
+    }
+    __syncthreads();
 }
 
 // One row of the batch: embedding (from `emb` or from `times` x `freqs_pi`) into x.
@@ -189,19 +193,19 @@ __global__ void __launch_bounds__(MLP_BLOCK) basis_mlp_fwd_kernel(MlpDims d, con
     load_embedding(d, m, emb, times, freqs_pi, x);
     __syncthreads();
     if (sv) for (int i = threadIdx.x; i < d.E; i += MLP_BLOCK) sv[d.sx + i] = x[i];
-    layer_rows<ACT, true>(P + d.w1, P + d.b1, x, d.E, d.W, a1, sv ? sv + d.s1 : nullptr);
-    __syncthreads();
-    layer_rows<ACT, true>(P + d.w2, P + d.b2, a1, d.W, d.W, a2, sv ? sv + d.s2 : nullptr);
-    __syncthreads();
-    layer_rows<ACT, true>(P + d.w3, P + d.b3, a2, d.W, d.H, a3, sv ? sv + d.s3 : nullptr);
-    __syncthreads();
+    layer_rows<false>(P + d.w1, P + d.b1, x, d.E, d.W, a1, 0);
+    activate<ACT>(a1, d.W, sv ? sv + d.s1 : nullptr);
+    layer_rows<false>(P + d.w2, P + d.b2, a1, d.W, d.W, a2, 0);
+    activate<ACT>(a2, d.W, sv ? sv + d.s2 : nullptr);
+    layer_rows<false>(P + d.w3, P + d.b3, a2, d.W, d.H, a3, 0);
+    activate<ACT>(a3, d.H, sv ? sv + d.s3 : nullptr);
     // the num_basis first head layers share their input: one [nb*Q, H] matrix
-    layer_rows<ACT, true>(P + d.h0, P + d.hb0, a3, d.H, d.NQ, au, sv ? sv + d.su : nullptr);
-    __syncthreads();
+    layer_rows<false>(P + d.h0, P + d.hb0, a3, d.H, d.NQ, au, 0);
+    activate<ACT>(au, d.NQ, sv ? sv + d.su : nullptr);
     // row 0 (the query time) may have its own destination, so that B(t) and the table land where the trainer keeps them
     float* out_row = basis_row0 ? (m == 0 ? basis_row0 : basis + (size_t)(m - 1) * d.NO) : basis + (size_t)m * d.NO;
-    // second head layers: block-diagonal, basis k reads its own Q hidden units
-    layer_rows<ACT, false>(P + d.h2, P + d.hb2, au, d.Q, d.NO, out_row, nullptr, d.O);
+    // second head layers: block-diagonal, basis k reads its own Q hidden units; no activation on the output
+    layer_rows<true>(P + d.h2, P + d.hb2, au, d.Q, d.NO, out_row, d.O);
 }
 
 // out[i] = act'(z[i]) * sum_j W[j, i] g[j]  (i < n_cols, j < n_rows): the transposed product of the backward pass.  The

@@ -10,7 +10,7 @@
 
 void rdg_set_error(const char* fmt, ...);
 void rdg_count_launches(int n);
-enum { RDG_TUN_PRE_FWD_MINB = 0, RDG_TUN_PRE_BWD_MINB = 1, RDG_TUN_PRE_GRID_CAP = 2, RDG_TUN_DTABLE_V1 = 3, RDG_TUN_COUNT = 4 };
+enum { RDG_TUN_PRE_GRID_CAP = 0, RDG_TUN_DTABLE_V1 = 1, RDG_TUN_COUNT = 2 };
 int rdg_tunable(int id);   // api.cu: environment default, rdg_set_tunable() override
 
 #define RDG_CHECK_ARG(cond, msg)                                   \

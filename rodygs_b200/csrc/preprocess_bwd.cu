@@ -57,11 +57,10 @@ __device__ __forceinline__ void sh_basis_grad(float x, float y, float z, float* 
     }
 }
 
-// MINB: CTAs per SM the register allocation must allow (2: 128 registers, the default; 3: 80 registers, A/B through the
-// "pre_bwd_minb" tunable).  Like the forward kernel this one is latency bound (ncu r01: 39 % of DRAM peak, long-scoreboard
-// stalls); double-buffering its SH rows was measured and did not help (0.489 vs 0.464 ms, profiles/r01_ab_v12_*.json).
-template <bool RAW, int DEG, int MINB>
-__global__ void __launch_bounds__(RDG_BLOCK, MINB) preprocess_bwd_kernel(const PreBwdParams p) {
+// Measured alternatives that did NOT help (B200, C4, profiles/r01_ab_v12_*.json, r01_ab_v13_*.json): double-buffering the SH
+// rows (0.489 vs 0.464 ms) and 3 CTAs per SM via __launch_bounds__(256, 3) (80 registers, 210 B of spills; 0.564 vs 0.467 ms).
+template <bool RAW, int DEG>
+__global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreBwdParams p) {
     extern __shared__ __align__(128) float smem[];
     constexpr int K = (DEG + 1) * (DEG + 1);
     constexpr int NREST = 3 * (K - 1);
@@ -550,13 +549,8 @@ template <bool RAW, int DEG>
 static int launch_bwd(const PreBwdParams& p, int grid, size_t smem, cudaStream_t s) {
     const int cap = rdg_tunable(RDG_TUN_PRE_GRID_CAP);
     if (cap > 0 && grid > cap) grid = cap;
-    if (rdg_tunable(RDG_TUN_PRE_BWD_MINB) == 3) {
-        RDG_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<RAW, DEG, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        preprocess_bwd_kernel<RAW, DEG, 3><<<grid, RDG_BLOCK, smem, s>>>(p);
-    } else {
-        RDG_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<RAW, DEG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        preprocess_bwd_kernel<RAW, DEG, 2><<<grid, RDG_BLOCK, smem, s>>>(p);
-    }
+    RDG_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<RAW, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    preprocess_bwd_kernel<RAW, DEG><<<grid, RDG_BLOCK, smem, s>>>(p);
     RDG_CHECK_LAUNCH();
     return RDG_OK;
 }

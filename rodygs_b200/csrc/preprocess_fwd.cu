@@ -28,13 +28,11 @@ struct PreFwdParams {
     int use_tma;
 };
 
-// MINB = CTAs per SM the register allocation must allow.  0: compiler's choice (86 registers -> 2 CTAs, 16 warps per SM);
-// 3: <= 80 registers -> 3 CTAs, 24 warps per SM.  ncu r01: the kernel is latency bound (long-scoreboard stalls on the
-// per-Gaussian fetch chain, 31 % issue-active, 36 % of DRAM peak), so resident warps are what it needs.  Double-buffering
-// the SH rows instead (two 46 KB buffers, next chunk's bulk load issued one chunk ahead) was measured and did NOT help
-// (0.266 vs 0.258 ms, profiles/r01_ab_v12_*.json): the bulk copy is not what the warps wait for.
-template <bool RAW, int DEG, int MINB>
-__global__ void __launch_bounds__(RDG_BLOCK, MINB) preprocess_fwd_kernel(const PreFwdParams p) {
+// Measured alternatives that did NOT help (B200, C4, profiles/r01_ab_v12_*.json, r01_ab_v13_*.json): double-buffering the SH
+// rows (next chunk's bulk load issued one chunk ahead; 0.266 vs 0.258 ms - the bulk copy is not what the warps wait for)
+// and forcing 3 CTAs per SM with __launch_bounds__(256, 3) (80 registers + spills; 0.302 vs 0.259 ms).
+template <bool RAW, int DEG>
+__global__ void __launch_bounds__(RDG_BLOCK) preprocess_fwd_kernel(const PreFwdParams p) {
     extern __shared__ __align__(128) float smem[];
     constexpr int K = (DEG + 1) * (DEG + 1);
     constexpr int NREST = 3 * (K - 1);
@@ -178,13 +176,8 @@ template <bool RAW, int DEG>
 static int launch_fwd(const PreFwdParams& p, int grid, size_t smem, cudaStream_t s) {
     const int cap = rdg_tunable(RDG_TUN_PRE_GRID_CAP);
     if (cap > 0 && grid > cap) grid = cap;
-    if (rdg_tunable(RDG_TUN_PRE_FWD_MINB) == 3) {
-        RDG_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<RAW, DEG, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        preprocess_fwd_kernel<RAW, DEG, 3><<<grid, RDG_BLOCK, smem, s>>>(p);
-    } else {
-        RDG_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<RAW, DEG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        preprocess_fwd_kernel<RAW, DEG, 0><<<grid, RDG_BLOCK, smem, s>>>(p);
-    }
+    RDG_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<RAW, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    preprocess_fwd_kernel<RAW, DEG><<<grid, RDG_BLOCK, smem, s>>>(p);
     RDG_CHECK_LAUNCH();
     return RDG_OK;
 }

@@ -194,14 +194,19 @@ def test_trainer_flow_feeds_table_and_returns_network_gradient():
     ((b_ref * d_bt).sum() + (table_ref * d_table).sum()).backward()
     # compared per packed block (the 16 heads stacked): the upstream gradients of a real render are tiny and of mixed
     # sign, so a single head's bias gradient can sit at the float32 cancellation noise of its own sum
+    # The deformation only sees B(t) - B(t_i), so dL/dB(t) = -sum_i dL/dtable[i] and e.g. the gradient of the last
+    # biases is analytically ZERO: both sides hold float32 cancellation noise there.  Hence an absolute floor scaled by
+    # the upstream gradient (rows x max|dL/dB| x a few ulp) next to the relative bound.
     want = deform.pack_state_dict({k: p.grad for k, p in twin.named_parameters()}, 53, 128, 16)
     got = mlp.grad.cpu()
+    floor = 4e-6 * (T + 1) * max(d_bt.abs().max().item(), d_table.abs().max().item())
     for name, (off, shape) in mlp.layout.items():
         n_el = 1
         for d in shape:
             n_el *= d
-        err = rel_err(got[off:off + n_el], want[off:off + n_el])
-        assert err < 5e-3, (name, err)
+        a, b = got[off:off + n_el], want[off:off + n_el]
+        err = (a - b).abs().max().item()
+        assert err < 5e-3 * b.abs().max().item() + floor, (name, err, b.abs().max().item(), floor)
 
     # one Adam step on the packed buffer == torch.optim.Adam on the twin (eps 1e-15, constant lr)
     before = mlp.params.detach().clone()
@@ -212,6 +217,5 @@ def test_trainer_flow_feeds_table_and_returns_network_gradient():
     assert not torch.equal(before, mlp.params.detach())
     for k, p in twin.named_parameters():
         # first Adam step = -lr * sign(g): compare where the gradient is well above its own parity error
-        sure = p.grad.abs() > 2e-2 * p.grad.abs().max()
-        assert sure.any()
+        sure = p.grad.abs() > max(2e-2 * p.grad.abs().max().item(), 50 * floor)
         assert ((after[k].cpu() - p.detach()).abs() * sure).max().item() < 2e-5, k
