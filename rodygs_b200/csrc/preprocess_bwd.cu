@@ -93,6 +93,21 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
     const int64_t cs = (sc.n_static + RDG_BLOCK - 1) / RDG_BLOCK, cd = (sc.n_dynamic + RDG_BLOCK - 1) / RDG_BLOCK;
     uint32_t phase = 0;
     bool store_pending = false;
+    // radius (visibility) and clamp flags of this thread's Gaussian are fetched ONE CHUNK AHEAD: everything else a thread
+    // loads hangs off `radius > 0`, so reading it at the top of its own chunk puts a DRAM round trip in front of the rest
+    auto chunk_slot = [&](int64_t chunk, int64_t& gi) -> bool {
+        const bool dyn_c = chunk >= cs;
+        const int64_t lb = (dyn_c ? chunk - cs : chunk) * RDG_BLOCK;
+        const int64_t n_c = dyn_c ? sc.n_dynamic : sc.n_static;
+        gi = (dyn_c ? sc.n_static : 0) + lb + threadIdx.x;
+        return lb + (int64_t)threadIdx.x < n_c;
+    };
+    int radius_pf = 0;
+    unsigned clamped_pf = 0;
+    if ((int64_t)blockIdx.x < cs + cd) {
+        int64_t gi;
+        if (chunk_slot(blockIdx.x, gi)) { radius_pf = p.geom.radii[gi]; clamped_pf = p.geom.clamped[gi]; }
+    }
     for (int64_t chunk = blockIdx.x; chunk < cs + cd; chunk += gridDim.x) {
         const bool dyn = chunk >= cs;
         const RdgSet& set = dyn ? sc.dy : sc.st;
@@ -103,8 +118,15 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
         const bool valid = (int)threadIdx.x < cnt;
         const int64_t local = lbase + threadIdx.x;
         const int64_t i = (dyn ? sc.n_static : 0) + local;
-        const int radius = valid ? p.geom.radii[i] : 0;
+        const int radius = radius_pf;
+        const unsigned cl_pf = clamped_pf;
         const bool vis = radius > 0;
+        radius_pf = 0;
+        clamped_pf = 0;
+        if (chunk + gridDim.x < cs + cd) {
+            int64_t gi;
+            if (chunk_slot(chunk + gridDim.x, gi)) { radius_pf = p.geom.radii[gi]; clamped_pf = p.geom.clamped[gi]; }
+        }
 
         // ---- stage the SH rest rows ----
         const bool full_rows = use_sh && set.sh_rest_stride == SH_ROW;
@@ -238,7 +260,7 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
         }
         if (vis) {
             if (use_sh) {
-                const unsigned cl = p.geom.clamped[i];
+                const unsigned cl = cl_pf;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) if (cl & (1u << c)) grgb[c] = 0.f;
                 float dx = a.x - campos[0], dy = a.y - campos[1], dz = a.z - campos[2];

@@ -94,6 +94,13 @@ __global__ void __launch_bounds__(RDG_BLOCK) preprocess_fwd_kernel(const PreFwdP
         bool vis = false;
         RdgAct a;
         float px = 0.f, py = 0.f, conA = 0.f, conB = 0.f, conC = 0.f, tz = 0.f;
+        // degree-0 SH coefficients: requested here with the geometry, not after the SH rows have arrived - otherwise they
+        // are one more exposed DRAM round trip at the end of every chunk (the kernel is latency bound)
+        float dc0 = 0.f, dc1 = 0.f, dc2 = 0.f;
+        if (valid && !sc.colors_precomp) {
+            const float* dc = set.sh_dc + local * set.sh_dc_stride;
+            dc0 = __ldg(dc); dc1 = __ldg(dc + 1); dc2 = __ldg(dc + 2);
+        }
         if (valid) {
             rdg_fetch<RAW>(sc, dyn, local, bt_s, a);
             if (p.geom.dbg_activated) {
@@ -140,13 +147,12 @@ __global__ void __launch_bounds__(RDG_BLOCK) preprocess_fwd_kernel(const PreFwdP
                 rgb[1] = sc.colors_precomp[i * 3 + 1];
                 rgb[2] = sc.colors_precomp[i * 3 + 2];
             } else {
-                const float* dc = set.sh_dc + local * set.sh_dc_stride;
                 float dx = a.x - campos[0], dy = a.y - campos[1], dz = a.z - campos[2];
                 const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
                 dx *= inv; dy *= inv; dz *= inv;
                 float b[K];
                 rdg_sh_basis<DEG>(dx, dy, dz, b);
-                rgb[0] = b[0] * __ldg(dc); rgb[1] = b[0] * __ldg(dc + 1); rgb[2] = b[0] * __ldg(dc + 2);
+                rgb[0] = b[0] * dc0; rgb[1] = b[0] * dc1; rgb[2] = b[0] * dc2;
                 const float* rest = sh_s + threadIdx.x * SH_ROW;
 #pragma unroll
                 for (int k = 1; k < K; ++k) {
