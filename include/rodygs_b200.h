@@ -162,6 +162,8 @@ uint64_t rdg_launch_count(void);
 /* A/B switches and test knobs of the launchers (process-wide; initial value from the environment variable RDG_<NAME>):
  *   "pre_grid_cap" > 0: cap on the persistent grid of the two preprocess kernels (tests: forces many chunks per CTA)
  *   "dtable_v1"    1: first version of the dL/dtable reduction
+ *   "diff_smem"    1 (default): the preprocess kernels keep B(t) - table rows in shared memory when num_times <= 140;
+ *                  0: every dynamic Gaussian gathers its 448-byte table row from global memory
  * Returns RDG_E_ARG for an unknown name. */
 int rdg_set_tunable(const char* name, int32_t value);
 

@@ -27,6 +27,7 @@ struct PreBwdParams {
     RdgSceneGrad gr;
     const float* acc;
     int use_tma;
+    int diff_smem;     // B(t) - table rows staged in shared memory (rdg_stage_diff)
     int dtab_atomic;   // no CSR: accumulate dL/dtable with global atomics from this kernel
 };
 
@@ -79,8 +80,11 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
     const float* V = cam.V;
     const float* P = cam.P;
 
-    if (deform)
+    float* diff_s = (deform && p.diff_smem) ? bt_s + RDG_NUM_BASIS_MAX * 7 : nullptr;
+    if (deform) {
         for (int e = threadIdx.x; e < sc.num_basis * 7; e += RDG_BLOCK) bt_s[e] = sc.basis_t[e];
+        if (diff_s) rdg_stage_diff(sc, sc.basis_t, diff_s, RDG_BLOCK);
+    }
     if (threadIdx.x == 0) rdg_mbar_init(&bar, 1);
     __syncthreads();
 
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
         float grgb[3] = {0.f, 0.f, 0.f};
         float* my_sh = sh_s + threadIdx.x * SH_ROW;
         if (vis) {
-            rdg_fetch<RAW>(sc, dyn, local, bt_s, a);
+            rdg_fetch<RAW>(sc, dyn, local, bt_s, a, diff_s);
             RdgProj pr;
             rdg_project(cam, a, p.view.scale_modifier, pr);
             const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.acc) + i * 3 + 0);
@@ -332,7 +336,19 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
 #pragma unroll
                     for (int k = 0; k < RDG_NUM_BASIS_MAX; ++k) dcf[k] = 0.f;
                     if (has_def) {
-                        if (sc.num_basis == RDG_NUM_BASIS_MAX) {
+                        if (sc.num_basis == RDG_NUM_BASIS_MAX && diff_s) {
+                            const float4* row4 = reinterpret_cast<const float4*>(diff_s + a.ti * RDG_DIFF_STRIDE);
+#pragma unroll
+                            for (int q = 0; q < 28; ++q) {
+                                const float4 v = row4[q];
+                                const float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                                for (int m = 0; m < 4; ++m) {
+                                    const int e = 4 * q + m;
+                                    dcf[e / 7] += r[m] * g7[e % 7];
+                                }
+                            }
+                        } else if (sc.num_basis == RDG_NUM_BASIS_MAX) {
                             const float4* row4 = reinterpret_cast<const float4*>(sc.table + (int64_t)a.ti * 112);
 #pragma unroll
                             for (int q = 0; q < 28; ++q) {
@@ -603,7 +619,12 @@ extern "C" int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, co
     const uintptr_t al = (uintptr_t)scene->st.sh_rest | (uintptr_t)scene->dy.sh_rest | (uintptr_t)grads->st.sh_rest |
                          (uintptr_t)grads->dy.sh_rest;
     p.use_tma = (al & 15u) == 0 ? 1 : 0;
-    const size_t smem = (RDG_BLOCK * SH_ROW + RDG_NUM_BASIS_MAX * 7) * sizeof(float);
+    size_t smem = (RDG_BLOCK * SH_ROW + RDG_NUM_BASIS_MAX * 7) * sizeof(float);
+    p.diff_smem = 0;
+    if (deform && scene->num_basis == RDG_NUM_BASIS_MAX && rdg_tunable(RDG_TUN_DIFF_SMEM) != 0) {
+        const size_t extra = (size_t)scene->num_times * RDG_DIFF_STRIDE * sizeof(float);
+        if (smem + extra <= RDG_PRE_SMEM_MAX) { p.diff_smem = 1; smem += extra; }
+    }
     const int64_t chunks = (scene->n_static + RDG_BLOCK - 1) / RDG_BLOCK + (scene->n_dynamic + RDG_BLOCK - 1) / RDG_BLOCK;
     const int64_t cap = (int64_t)RDG_SM_COUNT * 2;   // 2 CTAs per SM (register-limited), persistent
     const int grid = (int)(chunks < cap ? chunks : cap);

@@ -26,6 +26,7 @@ struct PreFwdParams {
     RdgView view;
     RdgGeom geom;
     int use_tma;
+    int diff_smem;   // B(t) - table rows staged in shared memory (rdg_stage_diff); the launcher sized the buffer
 };
 
 // Measured alternatives that did NOT help (B200, C4, profiles/r01_ab_v12_*.json, r01_ab_v13_*.json): double-buffering the SH
@@ -48,8 +49,11 @@ __global__ void __launch_bounds__(RDG_BLOCK) preprocess_fwd_kernel(const PreFwdP
     rdg_campos(cam, campos);
 
     const bool deform = RAW && sc.use_deform && sc.n_dynamic > 0;
-    if (deform)
+    float* diff_s = (deform && p.diff_smem) ? bt_s + RDG_NUM_BASIS_MAX * 7 : nullptr;
+    if (deform) {
         for (int e = threadIdx.x; e < sc.num_basis * 7; e += RDG_BLOCK) bt_s[e] = sc.basis_t[e];
+        if (diff_s) rdg_stage_diff(sc, sc.basis_t, diff_s, RDG_BLOCK);
+    }
     if (threadIdx.x == 0) rdg_mbar_init(&bar, 1);
     __syncthreads();
 
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(RDG_BLOCK) preprocess_fwd_kernel(const PreFwdP
             dc0 = __ldg(dc); dc1 = __ldg(dc + 1); dc2 = __ldg(dc + 2);
         }
         if (valid) {
-            rdg_fetch<RAW>(sc, dyn, local, bt_s, a);
+            rdg_fetch<RAW>(sc, dyn, local, bt_s, a, diff_s);
             if (p.geom.dbg_activated) {
                 float* d = p.geom.dbg_activated + i * 11;
                 d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.s[0]; d[4] = a.s[1]; d[5] = a.s[2];
@@ -230,10 +234,18 @@ extern "C" int rdg_preprocess_fwd(const RdgScene* scene, const RdgView* view, co
     // TMA needs 16-byte aligned global sources; torch allocations are, arbitrary views may not be
     const bool aligned = (((uintptr_t)scene->st.sh_rest | (uintptr_t)scene->dy.sh_rest) & 15u) == 0;
     p.use_tma = aligned ? 1 : 0;
-    const size_t smem = (RDG_BLOCK * SH_ROW + RDG_NUM_BASIS_MAX * 7) * sizeof(float);
+    size_t smem = (RDG_BLOCK * SH_ROW + RDG_NUM_BASIS_MAX * 7) * sizeof(float);
+    // B(t) - table rows in shared memory when the whole table fits next to the SH rows with 2 CTAs per SM (T <= 140)
+    p.diff_smem = 0;
+    if (deform && scene->num_basis == RDG_NUM_BASIS_MAX && rdg_tunable(RDG_TUN_DIFF_SMEM) != 0) {
+        const size_t extra = (size_t)scene->num_times * RDG_DIFF_STRIDE * sizeof(float);
+        if (smem + extra <= RDG_PRE_SMEM_MAX) { p.diff_smem = 1; smem += extra; }
+    }
     const int64_t chunks = (scene->n_static + RDG_BLOCK - 1) / RDG_BLOCK + (scene->n_dynamic + RDG_BLOCK - 1) / RDG_BLOCK;
-    // persistent grid: a multiple of the SM count (4 CTAs of 46 KB fit per SM)
-    const int grid = (int)(chunks < (int64_t)RDG_SM_COUNT * 4 ? chunks : (int64_t)RDG_SM_COUNT * 4);
+    // persistent grid: a multiple of the SM count.  2 CTAs are resident per SM (registers); with the staged difference
+    // table every CTA pays for filling it once, so the grid is exactly the resident set
+    const int64_t per_sm = p.diff_smem ? 2 : 4;
+    const int grid = (int)(chunks < (int64_t)RDG_SM_COUNT * per_sm ? chunks : (int64_t)RDG_SM_COUNT * per_sm);
     cudaStream_t s = (cudaStream_t)stream;
     if (geom->tile_count) {
         const int tiles = ((view->width + RDG_TILE - 1) / RDG_TILE) * ((view->height + RDG_TILE - 1) / RDG_TILE);

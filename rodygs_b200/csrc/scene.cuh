@@ -30,12 +30,40 @@ __device__ __forceinline__ float rdg_basis_diff(const RdgScene& sc, const float*
     return basis_t[k * 7 + j] - __ldg(sc.table + ((int64_t)ti * sc.num_basis + k) * 7 + j);
 }
 
-// delta[j] = sum_k c_k (B(t)[k][j] - table[ti][k][j]),  j = 0..6
-__device__ __forceinline__ void rdg_deform_delta(const RdgScene& sc, const float* basis_t, int ti, const float* c, float* d) {
+// Shared-memory copy of the differences B(t) - table[t'] for every frame t' (row stride RDG_DIFF_STRIDE floats).
+// ncu r01: the per-lane gathers of 448-byte table rows (28 LDG.128 per dynamic Gaussian, 32 different rows per warp
+// instruction = 32 L1 wavefronts each) kept the L1TEX pipe of both preprocess kernels 55-63 % busy - their top unit.  From
+// shared memory the same row costs 28 LDS.128 at ~2 wavefronts each (116-float stride: 29 x 16 B, odd in 16-byte units,
+// so the rows of the 8 lanes of a phase spread over all bank groups).
+#define RDG_DIFF_STRIDE 116
+__device__ __forceinline__ void rdg_stage_diff(const RdgScene& sc, const float* basis_t, float* diff_s, int nthreads) {
+    const int per_t = sc.num_basis * 7;
+    for (int idx = threadIdx.x; idx < sc.num_times * per_t; idx += nthreads) {
+        const int t = idx / per_t, e = idx - t * per_t;
+        diff_s[t * RDG_DIFF_STRIDE + e] = basis_t[e] - __ldg(sc.table + idx);
+    }
+}
+
+// delta[j] = sum_k c_k (B(t)[k][j] - table[ti][k][j]),  j = 0..6.  diff_s: rdg_stage_diff()'s copy, or NULL (then the
+// table row is gathered from global memory).  Same float operations either way: the results are bit-identical.
+__device__ __forceinline__ void rdg_deform_delta(const RdgScene& sc, const float* basis_t, int ti, const float* c, float* d,
+                                                 const float* diff_s = nullptr) {
 #pragma unroll
     for (int j = 0; j < 7; ++j) d[j] = 0.f;
     const float* row = sc.table + (int64_t)ti * sc.num_basis * 7;
-    if (sc.num_basis == RDG_NUM_BASIS_MAX) {
+    if (sc.num_basis == RDG_NUM_BASIS_MAX && diff_s) {
+        const float4* row4 = reinterpret_cast<const float4*>(diff_s + ti * RDG_DIFF_STRIDE);
+#pragma unroll
+        for (int q = 0; q < 28; ++q) {
+            const float4 v = row4[q];
+            const float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int e = 4 * q + m;
+                d[e % 7] += c[e / 7] * r[m];
+            }
+        }
+    } else if (sc.num_basis == RDG_NUM_BASIS_MAX) {
         const float4* row4 = reinterpret_cast<const float4*>(row);   // 112 floats = 28 float4
 #pragma unroll
         for (int q = 0; q < 28; ++q) {
@@ -55,7 +83,8 @@ __device__ __forceinline__ void rdg_deform_delta(const RdgScene& sc, const float
 }
 
 template <bool RAW>
-__device__ __forceinline__ void rdg_fetch(const RdgScene& sc, bool dyn, int64_t local, const float* basis_t, RdgAct& a) {
+__device__ __forceinline__ void rdg_fetch(const RdgScene& sc, bool dyn, int64_t local, const float* basis_t, RdgAct& a,
+                                          const float* diff_s = nullptr) {
     a.dyn = dyn;
     a.local = local;
     const RdgSet& set = dyn ? sc.dy : sc.st;
@@ -89,7 +118,7 @@ __device__ __forceinline__ void rdg_fetch(const RdgScene& sc, bool dyn, int64_t 
                 for (int k = 0; k < RDG_NUM_BASIS_MAX; ++k) a.c[k] = k < sc.num_basis ? __ldg(pc + k) : 0.f;
             }
             float d[7];
-            rdg_deform_delta(sc, basis_t, a.ti, a.c, d);
+            rdg_deform_delta(sc, basis_t, a.ti, a.c, d, diff_s);
             a.x += d[0] * sc.spatial_lr_scale;
             a.y += d[1] * sc.spatial_lr_scale;
             a.z += d[2] * sc.spatial_lr_scale;

@@ -218,17 +218,18 @@ def test_known_answer_single_gaussian():
 def _tunables():
     from rodygs_b200 import _lib
     yield _lib.set_tunable
-    for name, v in (("pre_grid_cap", 0), ("dtable_v1", 0)):
+    for name, v in (("pre_grid_cap", 0), ("dtable_v1", 0), ("diff_smem", 1)):
         _lib.set_tunable(name, v)
 
 
-@pytest.mark.parametrize("n,cap,dt1", [(3000, 2, 0), (2602, 3, 0), (2602, 2, 1), (3000, 0, 1)])
-def test_fused_path_multi_chunk_staging(_tunables, n, cap, dt1):
+@pytest.mark.parametrize("n,cap,dt1,diff", [(3000, 2, 0, 1), (2602, 3, 0, 0), (2602, 2, 1, 1), (3000, 0, 1, 0)])
+def test_fused_path_multi_chunk_staging(_tunables, n, cap, dt1, diff):
     """The persistent preprocess kernels with several chunks per CTA (grid capped), chunks whose row count is not a
     multiple of 4 (2602 -> 1301 per model -> a 21-row last chunk that cannot be bulk-copied, in the middle of a CTA's
     chunk sequence), and both dL/dtable reductions."""
     _tunables("pre_grid_cap", cap)
     _tunables("dtable_v1", dt1)
+    _tunables("diff_smem", diff)     # B(t) - table rows from shared memory / gathered from global memory
     test_fused_dynamic_path_matches_oracle_chain(n)
     test_fused_path_bitexact_given_its_own_activations(n)
 
