@@ -621,7 +621,8 @@ extern "C" int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, co
     p.use_tma = (al & 15u) == 0 ? 1 : 0;
     size_t smem = (RDG_BLOCK * SH_ROW + RDG_NUM_BASIS_MAX * 7) * sizeof(float);
     p.diff_smem = 0;
-    if (deform && scene->num_basis == RDG_NUM_BASIS_MAX && rdg_tunable(RDG_TUN_DIFF_SMEM) != 0) {
+    if (deform && scene->num_basis == RDG_NUM_BASIS_MAX && rdg_tunable(RDG_TUN_DIFF_SMEM) != 0 &&
+        (((uintptr_t)scene->basis_t | (uintptr_t)scene->table) & 15u) == 0) {
         const size_t extra = (size_t)scene->num_times * RDG_DIFF_STRIDE * sizeof(float);
         if (smem + extra <= RDG_PRE_SMEM_MAX) { p.diff_smem = 1; smem += extra; }
     }

@@ -237,7 +237,8 @@ extern "C" int rdg_preprocess_fwd(const RdgScene* scene, const RdgView* view, co
     size_t smem = (RDG_BLOCK * SH_ROW + RDG_NUM_BASIS_MAX * 7) * sizeof(float);
     // B(t) - table rows in shared memory when the whole table fits next to the SH rows with 2 CTAs per SM (T <= 140)
     p.diff_smem = 0;
-    if (deform && scene->num_basis == RDG_NUM_BASIS_MAX && rdg_tunable(RDG_TUN_DIFF_SMEM) != 0) {
+    if (deform && scene->num_basis == RDG_NUM_BASIS_MAX && rdg_tunable(RDG_TUN_DIFF_SMEM) != 0 &&
+        (((uintptr_t)scene->basis_t | (uintptr_t)scene->table) & 15u) == 0) {
         const size_t extra = (size_t)scene->num_times * RDG_DIFF_STRIDE * sizeof(float);
         if (smem + extra <= RDG_PRE_SMEM_MAX) { p.diff_smem = 1; smem += extra; }
     }

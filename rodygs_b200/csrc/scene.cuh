@@ -36,11 +36,14 @@ __device__ __forceinline__ float rdg_basis_diff(const RdgScene& sc, const float*
 // shared memory the same row costs 28 LDS.128 at ~2 wavefronts each (116-float stride: 29 x 16 B, odd in 16-byte units,
 // so the rows of the 8 lanes of a phase spread over all bank groups).
 #define RDG_DIFF_STRIDE 116
+// Only used with num_basis == RDG_NUM_BASIS_MAX: a row is 112 floats = 28 float4 (compile-time divisor).
 __device__ __forceinline__ void rdg_stage_diff(const RdgScene& sc, const float* basis_t, float* diff_s, int nthreads) {
-    const int per_t = sc.num_basis * 7;
-    for (int idx = threadIdx.x; idx < sc.num_times * per_t; idx += nthreads) {
-        const int t = idx / per_t, e = idx - t * per_t;
-        diff_s[t * RDG_DIFF_STRIDE + e] = basis_t[e] - __ldg(sc.table + idx);
+    const float4* tab4 = reinterpret_cast<const float4*>(sc.table);
+    const float4* bt4 = reinterpret_cast<const float4*>(basis_t);
+    for (int idx = threadIdx.x; idx < sc.num_times * 28; idx += nthreads) {
+        const int t = idx / 28, q = idx - t * 28;
+        const float4 b = __ldg(bt4 + q), r = __ldg(tab4 + idx);
+        *reinterpret_cast<float4*>(diff_s + t * RDG_DIFF_STRIDE + 4 * q) = make_float4(b.x - r.x, b.y - r.y, b.z - r.z, b.w - r.w);
     }
 }
 
