@@ -268,12 +268,12 @@ def run_ours(args, rank, world, local_rank):
             if k == 0:
                 prefetch(0)
             torch.cuda.current_stream().wait_event(ready[k % 2])
-            prefetch(k + 1)
             vm, pm, bt, gt, gtd = slots[k % 2]
         step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, bt, gt, gtd, forward_only=args.forward_only,
                               dcolor_slot=0 if factored else None)
         if e2e:
             consumed[k % 2].record()
+            prefetch(k + 1)    # enqueued after this step's launches: the GPU is never idle while the copies are set up
         if world > 1:
             if args.plain_allreduce:
                 step.allreduce_grads(1.0 / world)

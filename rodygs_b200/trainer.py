@@ -131,6 +131,7 @@ class SplatTrainStep:
         self.num_basis = scene["motion_coeff"].shape[-1]
         self.T = scene["table"].shape[0]
         self.layout, total = flat_layout(ns, nd, self.num_basis, self.T)
+        self._set_cache = {}
         self.params = torch.zeros(total, dtype=torch.float32, device=self.dev)
         self.grads = torch.zeros(total, dtype=torch.float32, device=self.dev)
         for tag in ("static", "dynamic"):
@@ -164,6 +165,16 @@ class SplatTrainStep:
     def _set(self, tag: str) -> Optional[SetArgs]:
         if (self.ns if tag == "static" else self.nd) == 0:
             return None
+        # the views only change when the flat buffers are rebuilt (_load_scene): building them every step costs ~50 us
+        # of host time in front of the step's first launch
+        cached = self._set_cache.get(tag)
+        if cached is not None and cached[0] is self.params:
+            return cached[1]
+        out = self._make_set(tag)
+        self._set_cache[tag] = (self.params, out)
+        return out
+
+    def _make_set(self, tag: str) -> SetArgs:
         return SetArgs(xyz=self.p(f"{tag}.xyz"), scaling=self.p(f"{tag}.scaling"), rotation=self.p(f"{tag}.rotation"),
                        opacity=self.p(f"{tag}.opacity"), sh_dc=self.p(f"{tag}.features_dc"),
                        sh_rest=self.p(f"{tag}.features_rest"), sh_dc_stride=3, sh_rest_stride=45)
