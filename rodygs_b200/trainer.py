@@ -12,6 +12,7 @@ gloo in the CPU tests).  Pose gradients and the means2D sink stay rank-local.
 from __future__ import annotations
 
 import ctypes as C
+import copy
 import math
 from typing import Dict, List, Optional, Tuple
 
@@ -182,6 +183,14 @@ class SplatTrainStep:
     def _setgrad(self, tag: str) -> SetGrads:
         if (self.ns if tag == "static" else self.nd) == 0:
             return SetGrads()
+        key = ("grad", tag, self.grads.data_ptr())     # self.grads is swapped for a second buffer when accumulating
+        out = self._set_cache.get(key)
+        if out is None:
+            out = self._make_setgrad(tag)
+            self._set_cache[key] = out
+        return copy.copy(out)                          # callers null some fields (factored exchange): a shallow copy
+
+    def _make_setgrad(self, tag: str) -> SetGrads:
         return SetGrads(xyz=self.g(f"{tag}.xyz"), scaling=self.g(f"{tag}.scaling"), rotation=self.g(f"{tag}.rotation"),
                         opacity=self.g(f"{tag}.opacity"), sh_dc=self.g(f"{tag}.features_dc"),
                         sh_rest=self.g(f"{tag}.features_rest"))
