@@ -234,11 +234,16 @@ def test_fused_path_multi_chunk_staging(_tunables, n, cap, dt1, diff):
     test_fused_path_bitexact_given_its_own_activations(n)
 
 
-def test_fused_dynamic_path_matches_oracle_chain(n=3000):
+def test_fused_path_with_more_frames_than_the_shared_memory_table_holds():
+    """num_times = 150 > 140: the launchers fall back from the staged B(t) - table rows to per-Gaussian gathers."""
+    test_fused_dynamic_path_matches_oracle_chain(2400, T=150)
+
+
+def test_fused_dynamic_path_matches_oracle_chain(n=3000, T=6):
     """Raw parameters + deformation fused in the kernel vs the reference chain on the CPU
     (activations -> deformation -> concat -> rasterize), forward and all gradients."""
     from rodygs_b200.dynamic import GaussianParams, render_dynamic
-    H, W, T = 96, 128, 6
+    H, W = 96, 128
     sc, cam = helpers.small_scene(n, H, W, T, seed=21)
     bg = torch.tensor([0.0, 0.0, 0.0])
     up = _upstream_grads(H, W)
