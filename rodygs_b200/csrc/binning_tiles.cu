@@ -24,6 +24,11 @@
 #include "common.cuh"
 
 #define TS_BINS 256
+// One fill counter per 128-byte line.  Packed (32 counters per line) the 8160 counters of a 1080p frame are 255 lines, which
+// the address hash spreads unevenly over the L2 slices: ncu r01 showed the busiest slice at 96 % while the average was
+// 55 % - the placement pass was bound by its hottest slice, not by atomic latency (four requests in flight per lane
+// instead of one changed nothing).
+#define TP_FILL_STRIDE 32
 #define TS_TIE_FIXUP_MAX 64
 
 // ------------------------------------------------------------ tile segments ----
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(RDG_BLOCK) tile_place_kernel(int64_t n, const 
             uint32_t slot[TP_UNROLL], base[TP_UNROLL];
 #pragma unroll
             for (int u = 0; u < TP_UNROLL; ++u) {
-                slot[u] = act[u] ? atomicAdd(&tile_fill[tile[u]], 1u) : 0u;
+                slot[u] = act[u] ? atomicAdd(&tile_fill[(size_t)tile[u] * TP_FILL_STRIDE], 1u) : 0u;
                 base[u] = act[u] ? __ldg(tile_off + tile[u]) : 0u;
             }
 #pragma unroll
@@ -345,7 +350,7 @@ static TileLayout tile_layout(int64_t d_cap, int32_t height, int32_t width) {
     L.tiles = ((width + RDG_TILE - 1) / RDG_TILE) * ((height + RDG_TILE - 1) / RDG_TILE);
     int64_t off = 0;
     L.tile_off = off;  off += rdg_align_up((int64_t)(L.tiles + 1) * 4, 256);
-    L.tile_fill = off; off += rdg_align_up((int64_t)L.tiles * 4, 256);
+    L.tile_fill = off; off += rdg_align_up((int64_t)L.tiles * TP_FILL_STRIDE * 4, 256);
     L.pairs = off;     off += rdg_align_up(d_cap * 8, 256);
     L.pairs_tmp = off; off += rdg_align_up(d_cap * 8, 256);
     L.total = off;
@@ -386,7 +391,7 @@ extern "C" int rdg_bin_tiles(int64_t n, const RdgGeom* geom, int32_t height, int
     uint64_t* pairs = (uint64_t*)(ws + L.pairs);
     uint64_t* pairs_tmp = (uint64_t*)(ws + L.pairs_tmp);
     const int gx = (width + RDG_TILE - 1) / RDG_TILE, gy = (height + RDG_TILE - 1) / RDG_TILE;
-    RDG_CUDA(cudaMemsetAsync(tile_fill, 0, (size_t)L.tiles * sizeof(uint32_t), s));
+    RDG_CUDA(cudaMemsetAsync(tile_fill, 0, (size_t)L.tiles * TP_FILL_STRIDE * sizeof(uint32_t), s));
     tile_scan_kernel<<<1, 1024, 0, s>>>(geom->tile_count, L.tiles, tile_off, bins->num_rendered, (uint32_t)d_cap,
                                         bins->tile_order);
     {
