@@ -10,7 +10,7 @@ import sys
 STAGE = {"preprocess_fwd_kernel": "preprocess_fwd", "tile_scan_kernel": "bin", "tile_place_kernel": "bin",
          "tile_sort_kernel": "bin", "blend_fwd_kernel": "blend_fwd", "ssim_fwd_kernel": "loss", "ssim_bwd_kernel": "loss",
          "loss_finalize_kernel": "loss", "blend_bwd_kernel": "blend_bwd", "preprocess_bwd_kernel": "preprocess_bwd",
-         "dtable_kernel": "preprocess_bwd"}
+         "dtable_kernel": "preprocess_bwd", "dtable2_kernel": "preprocess_bwd"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
@@ -32,6 +32,15 @@ def main():
             key = name.split("(")[0].replace("void ", "").strip()
             per_kernel.setdefault(key, []).append(tot)
     kern = {k: sum(v) / len(v) for k, v in per_kernel.items()}          # mean over the captured launches
+    out_path0 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "traffic.json")
+    if os.path.exists(out_path0):                                        # keep kernels an earlier capture recorded
+        old = json.load(open(out_path0)).get(cfg + "_kernels", {})
+        fresh = {k.split("<")[0] for k in kern}
+        if "dtable2_kernel" in fresh:
+            fresh.add("dtable_kernel")                                   # replaced by dtable2
+        for k, b in old.items():
+            if k.split("<")[0] not in fresh:
+                kern[k] = float(b)
     stage = {}
     for k, b in kern.items():
         s = STAGE[k.split("<")[0]]
