@@ -17,6 +17,7 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 def main():
     cfg, paths = sys.argv[1], sys.argv[2:]
     per_kernel = {}
+    per_inst = {}
     for p in paths:
         rows = list(csv.reader(open(p)))
         hdr, units = rows[0], rows[1]
@@ -31,6 +32,8 @@ def main():
                 tot += float(r[idx[m]].replace(",", "")) * UNIT[units[idx[m]]]
             key = name.split("(")[0].replace("void ", "").strip()
             per_kernel.setdefault(key, []).append(tot)
+            if "smsp__inst_executed.sum" in idx:
+                per_inst.setdefault(key, []).append(float(r[idx["smsp__inst_executed.sum"]].replace(",", "")))
     kern = {k: sum(v) / len(v) for k, v in per_kernel.items()}          # mean over the captured launches
     out_path0 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "traffic.json")
     if os.path.exists(out_path0):                                        # keep kernels an earlier capture recorded
@@ -49,6 +52,9 @@ def main():
     data = json.load(open(out_path)) if os.path.exists(out_path) else {}
     data[cfg] = {s: int(b) for s, b in stage.items()}
     data[cfg + "_kernels"] = {k: int(b) for k, b in kern.items()}
+    inst = dict(data.get(cfg + "_warp_inst", {}))                        # warp instructions per launch (issue roofline)
+    inst.update({k: int(sum(v) / len(v)) for k, v in per_inst.items()})
+    data[cfg + "_warp_inst"] = inst
     data["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full --clock-control none), summed over "
                      "the kernels of each bench stage; written by tools/make_traffic.py")
     json.dump(data, open(out_path, "w"), indent=1, sort_keys=True)
