@@ -504,94 +504,73 @@ __global__ void __launch_bounds__(128) dtable2_kernel(const int32_t* __restrict_
     __shared__ __align__(16) float g_s[DT2_TILE * DT2_GS];
     const int lane = threadIdx.x & 31, kq = threadIdx.x >> 5;
     const int items = num_times * slices;
-    const int stride = slices * DT2_TILE;
-    float bas[4][7], acc[4][7];
+    float bas[4][7];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int j = 0; j < 7; ++j) bas[a][j] = acc[a][j] = 0.f;
-
-    // The CTA's work is a flat sequence of rounds (128 Gaussians of one frame each).  The rows of round r + 1 are
-    // requested (index load, then six 16-byte gathers per thread) before round r is reduced, so the two dependent DRAM
-    // round trips of a round hide behind the previous round's shared-memory pass.
-    struct Cursor { int item, t, base, end; };
-    auto seek = [&](Cursor& c) {          // first non-empty round at or after (c.item, c.base)
-        while (c.item < items && c.base >= c.end) {
-            c.item += gridDim.x;
-            if (c.item < items) {
-                c.t = c.item / slices;
-                const int sl = c.item - c.t * slices;
-                c.base = __ldg(offsets + c.t) + sl * DT2_TILE;
-                c.end = __ldg(offsets + c.t + 1);
-            }
-        }
-    };
-    float4 rc[4], rga, rgb;
-    auto fetch = [&](const Cursor& c) {
-        rc[0] = rc[1] = rc[2] = rc[3] = rga = rgb = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int i = c.base + (int)threadIdx.x;
-        if (c.item < items && i < c.end) {
-            const int64_t id = __ldg(order + i);
-            if (num_basis == 16) {
-                const float4* cr = reinterpret_cast<const float4*>(coeff + id * 16);
-                rc[0] = __ldg(cr); rc[1] = __ldg(cr + 1); rc[2] = __ldg(cr + 2); rc[3] = __ldg(cr + 3);
-            } else {
-                float tmp[16];
+        for (int j = 0; j < 7; ++j) bas[a][j] = 0.f;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int t = item / slices, sl = item - t * slices;
+        const int beg = offsets[t], end = offsets[t + 1];
+        float acc[4][7];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) tmp[k] = k < num_basis ? __ldg(coeff + id * num_basis + k) : 0.f;
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) rc[q] = make_float4(tmp[4 * q], tmp[4 * q + 1], tmp[4 * q + 2], tmp[4 * q + 3]);
-            }
-            const float4* gr = reinterpret_cast<const float4*>(g7 + id * 8);
-            rga = __ldg(gr); rgb = __ldg(gr + 1);
-        }
-    };
-    Cursor cur;
-    cur.item = (int)blockIdx.x - (int)gridDim.x; cur.t = 0; cur.base = 0; cur.end = 0;   // seek() steps onto the first item
-    seek(cur);
-    fetch(cur);
-    while (cur.item < items) {
-        Cursor nxt = cur;
-        nxt.base += stride;
-        seek(nxt);
-        __syncthreads();                       // the previous round's readers are done
-        {
-            float4* cd = reinterpret_cast<float4*>(c_s + threadIdx.x * DT2_CS);
-            cd[0] = rc[0]; cd[1] = rc[1]; cd[2] = rc[2]; cd[3] = rc[3];
-            float4* gd = reinterpret_cast<float4*>(g_s + threadIdx.x * DT2_GS);
-            gd[0] = rga; gd[1] = rgb;
-        }
-        __syncthreads();
-        fetch(nxt);                            // in flight while this round is reduced
+            for (int j = 0; j < 7; ++j) acc[a][j] = 0.f;
+        for (int base = beg + sl * DT2_TILE; base < end; base += slices * DT2_TILE) {
+            const int cnt = min(DT2_TILE, end - base);
+            __syncthreads();                       // the previous round's readers are done
+            {
+                const int i = threadIdx.x;
+                float4 c[4], ga, gb;
+                c[0] = c[1] = c[2] = c[3] = ga = gb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < cnt) {
+                    const int64_t id = order[base + i];
+                    if (num_basis == 16) {
+                        const float4* cr = reinterpret_cast<const float4*>(coeff + id * 16);
+                        c[0] = __ldg(cr); c[1] = __ldg(cr + 1); c[2] = __ldg(cr + 2); c[3] = __ldg(cr + 3);
+                    } else {
+                        float tmp[16];
 #pragma unroll
-        for (int r = 0; r < DT2_TILE / 32; ++r) {
-            const int g = lane + 32 * r;
-            const float4 c4 = *reinterpret_cast<const float4*>(c_s + g * DT2_CS + 4 * kq);
-            const float4 ga = *reinterpret_cast<const float4*>(g_s + g * DT2_GS);
-            const float4 gb = *reinterpret_cast<const float4*>(g_s + g * DT2_GS + 4);
-            const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-            const float gg[7] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z};
+                        for (int k = 0; k < 16; ++k) tmp[k] = k < num_basis ? __ldg(coeff + id * num_basis + k) : 0.f;
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int j = 0; j < 7; ++j) acc[a][j] = fmaf(cc[a], gg[j], acc[a][j]);
-        }
-        if (nxt.item != cur.item) {
-            // item total over the 32 lanes (butterfly: every lane ends with the sum); lane 0 adds it to dL/dtable[t]
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    float v = acc[a][j];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    bas[a][j] += v;
-                    acc[a][j] = 0.f;
-                    const int k = 4 * kq + a;
-                    if (lane == 0 && k < num_basis && v != 0.f) atomicAdd(&dtable[((int64_t)cur.t * num_basis + k) * 7 + j], -v);
+                        for (int q = 0; q < 4; ++q) c[q] = make_float4(tmp[4 * q], tmp[4 * q + 1], tmp[4 * q + 2], tmp[4 * q + 3]);
+                    }
+                    const float4* gr = reinterpret_cast<const float4*>(g7 + id * 8);
+                    ga = __ldg(gr); gb = __ldg(gr + 1);
                 }
+                float4* cd = reinterpret_cast<float4*>(c_s + i * DT2_CS);
+                cd[0] = c[0]; cd[1] = c[1]; cd[2] = c[2]; cd[3] = c[3];
+                float4* gd = reinterpret_cast<float4*>(g_s + i * DT2_GS);
+                gd[0] = ga; gd[1] = gb;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < DT2_TILE / 32; ++r) {
+                const int g = lane + 32 * r;
+                const float4 c4 = *reinterpret_cast<const float4*>(c_s + g * DT2_CS + 4 * kq);
+                const float4 ga = *reinterpret_cast<const float4*>(g_s + g * DT2_GS);
+                const float4 gb = *reinterpret_cast<const float4*>(g_s + g * DT2_GS + 4);
+                const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+                const float gg[7] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) acc[a][j] = fmaf(cc[a], gg[j], acc[a][j]);
+            }
         }
-        cur = nxt;
+        // item total over the 32 lanes (butterfly: every lane ends with the sum); lane 0 adds it to dL/dtable[t]
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                float v = acc[a][j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                bas[a][j] += v;
+                const int k = 4 * kq + a;
+                if (lane == 0 && k < num_basis && v != 0.f) atomicAdd(&dtable[((int64_t)t * num_basis + k) * 7 + j], -v);
+            }
     }
     if (dbasis && lane == 0) {
 #pragma unroll
