@@ -418,6 +418,12 @@ class SplatTrainStep:
         """dL/dB(t) and dL/dtable of the flat GRADIENT buffer -> mlp.grad (two launches, deterministic)."""
         return self.mlp.backward_rows(self.g("table"), d_row0=self.g("basis_t"), accumulate=accumulate)
 
+    def allreduce_basis_grads(self, scale: Optional[float] = None):
+        """Data parallel: sum the network's packed gradient (68 656 floats) over the ranks.  Call basis_backward() on the
+        rank-LOCAL dL/dB(t) / dL/dtable first, i.e. before exchange_grads() / allreduce_grads(): B(t) belongs to the rank's
+        own view time, so its gradient must go through the network before anything is summed across views."""
+        return allreduce_flat(self.mlp.grad, scale, self.pg)
+
     def basis_optimizer_step(self, iteration: int, grad_scale: float = 1.0):
         """Adam step of the "deform_network" group (append_motion_optim, src/trainer/rodygs_dynamic.py:101-106: one group,
         eps 1e-15) on the packed buffer - one rdg_adam launch.  The learning rate is constant = deform_lr_init:

@@ -41,6 +41,8 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(_lib.RdgSetGrad) == 6 * 8
     assert C.sizeof(_lib.RdgSceneGrad) == 2 * 48 + 8 * 8
     assert C.sizeof(_lib.RdgScene) == 16 + 2 * 56 + 8 + 8 + 16 + 4 * 8 + 8 + 2 * 8
+    assert C.sizeof(_lib.RdgBasisMlp) == 6 * 4 + 7 * 8
+    assert C.sizeof(_lib.RdgAdamGroup) == 24 and C.sizeof(_lib.RdgDensifyField) == 24
 
 
 def test_argument_errors_are_reported_without_a_gpu():
@@ -137,3 +139,15 @@ def test_algorithmic_bytes_formula_matches_baseline_md():
     # BASELINE.md §3.3 worked examples
     assert abs(algorithmic_bytes(2_000_000, 2_000_000, 1_000_000, 8_000_000, 2_073_600) / 1e9 - 3.34) < 0.03
     assert abs(algorithmic_bytes(6_000_000, 6_000_000, 3_000_000, 24_000_000, 2_073_600, forward_only=True) / 1e9 - 4.25) < 0.03
+
+
+def test_tunables_are_validated_and_settable_without_a_gpu():
+    from rodygs_b200 import _lib
+    lib = _lib.load()
+    assert lib.rdg_set_tunable(b"no_such_knob", 1) == -1
+    assert b"unknown tunable" in lib.rdg_last_error()
+    for name, default in (("pre_grid_cap", 0), ("dtable_v1", 0), ("diff_smem", 1)):
+        _lib.set_tunable(name, 5)
+        _lib.set_tunable(name, default)
+    with pytest.raises(RuntimeError, match="unknown tunable"):
+        _lib.set_tunable("nope", 0)
