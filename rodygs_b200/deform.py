@@ -24,7 +24,6 @@ from typing import Dict, Optional, Tuple
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 
 class TimestepEmbedder(nn.Module):

@@ -15,7 +15,6 @@ visiting the views one after the other - and the split noise comes from a genera
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Dict, Optional, Tuple
 
 import torch

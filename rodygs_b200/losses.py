@@ -9,7 +9,6 @@ One CUDA call computes the loss *and* its gradient w.r.t. the prediction
 """
 from __future__ import annotations
 
-import ctypes as C
 import math
 from typing import Optional
 

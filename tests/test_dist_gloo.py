@@ -82,8 +82,8 @@ def test_view_sharded_allreduce_matches_sequential():
         p.start()
     got = ret.get(timeout=240)
     for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+        p.join(timeout=180)
+        assert p.exitcode == 0, f"worker exit code {p.exitcode}"
     sc = synthetic.make_scene(N, H, W, T, seed=3)
     layout, total = flat_layout(sc["static"]["xyz"].shape[0], sc["dynamic"]["xyz"].shape[0], 16, T)
     ref = torch.zeros(total)
@@ -91,7 +91,10 @@ def test_view_sharded_allreduce_matches_sequential():
         ref += _view_grads(sc, v, layout, total)
     ref /= VIEWS
     assert ref.abs().max() > 0
-    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-8)
+    # two ranks sum two views each and then add across ranks; the reference sums the four views in order (and the workers run
+    # with 2 threads, this process with all cores): equal up to float32 summation order
+    assert helpers.rel_err(got, ref) < 1e-5
+    assert torch.allclose(got, ref, rtol=1e-3, atol=1e-7)
 
 
 def _worker_factored(rank, world, port, ret):
@@ -143,8 +146,8 @@ def test_factored_sh_exchange_matches_sequential():
         p.start()
     got = ret.get(timeout=240)
     for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+        p.join(timeout=180)
+        assert p.exitcode == 0, f"worker exit code {p.exitcode}"
     sc = synthetic.make_scene(N, H, W, T, seed=3)
     layout, total = flat_layout(sc["static"]["xyz"].shape[0], sc["dynamic"]["xyz"].shape[0], 16, T)
     ref = torch.zeros(total)
