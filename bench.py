@@ -101,13 +101,23 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_rate(max_frames: int = 8):
-    """PyTorch-CPU oracle on BASELINE config 1; returns (it/s at the sample, description, bytes per iteration)."""
+def cpu_oracle_rate(cfg: str = "c4_iphone", max_frames: int = 4):
+    """PyTorch-CPU oracle on a bounded sample of workload `cfg`: a 256x256-pixel window (256 tiles) with the workload's own
+    number of Gaussians per tile (N' = N * 256 / tiles - the scene generator draws scales for a fixed screen radius, so the
+    per-tile list length, which is what the blend cost depends on, matches: 737 entries per tile against 723 at BASELINE
+    config 4), same T, same SH degree, same loss terms.  BASELINE config 1 is its own sample.
+    Returns (it/s at the sample, description, algorithmic bytes per iteration of the sample)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle import deform_oracle as do, loss_oracle as lo, splat_oracle as so
     from rodygs_b200 import synthetic
     torch.set_num_threads(os.cpu_count() or 1)
-    N, H, W, T, _ = synthetic.CONFIGS["c1_cpu"]
+    Nf, Hf, Wf, T, _ = synthetic.CONFIGS[cfg]
+    tiles_f = ((Hf + 15) // 16) * ((Wf + 15) // 16)
+    if cfg == "c1_cpu":
+        N, H, W = Nf, Hf, Wf
+    else:
+        H = W = 256
+        N = max(1000, int(round(Nf * 256 / tiles_f)))
     sc = synthetic.make_scene(N, H, W, T, seed=0)
     g = torch.Generator().manual_seed(99)
     gt = torch.rand(3, H, W, generator=g)
@@ -134,8 +144,9 @@ def cpu_oracle_rate(max_frames: int = 8):
             stats = (N, int((out.radii > 0).sum()), N // 2, int(out.bn.keys.numel()), H * W)
     rate = len(times) / sum(times)
     nbytes = synthetic.algorithmic_bytes(*stats)
-    desc = (f"oracle (PyTorch-CPU, fp32) on BASELINE config 1: {N} Gaussians (50% dynamic), {H}x{W}, "
-            f"{len(times)} frames fwd+loss+bwd after 1 warm-up frame; {rate:.3f} it/s at that size")
+    desc = (f"oracle (PyTorch-CPU, fp32) on a {256 / tiles_f:.4f} sample of {cfg} at the same Gaussian density per tile: {N} "
+            f"Gaussians (50% dynamic), {H}x{W} window ({(H // 16) * (W // 16)} of {tiles_f} tiles, {stats[3] / ((H // 16) * (W // 16)):.0f} "
+            f"list entries per tile), T={T}, {len(times)} frames fwd+loss+bwd after 1 warm-up frame; {rate:.3f} it/s at that size")
     return rate, desc, nbytes
 
 
@@ -143,7 +154,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     from rodygs_b200 import synthetic
-    rate, desc, sample_bytes = cpu_oracle_rate(max(2, min(8, args.steps)))
+    rate, desc, sample_bytes = cpu_oracle_rate(args.config, max(2, min(4, args.steps)))
     N, H, W, T, _ = synthetic.CONFIGS[args.config]
     full_bytes = synthetic.algorithmic_bytes(N, int(0.9 * N), N // 2, 3 * N, H * W)
     value = rate * sample_bytes / full_bytes
@@ -152,7 +163,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.config), "note": "CPU arm: bounded sample scaled by algorithmic bytes"},
+        "config": {"workload": workload_name(args.config), "note": "CPU arm: 256x256-pixel window at the workload's Gaussian density per tile, scaled by algorithmic bytes"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": desc + f"; scaled by algorithmic bytes {sample_bytes / full_bytes:.3e} to {args.config}",
                          "sample_value": rate},
@@ -417,7 +428,7 @@ def run_ours(args, rank, world, local_rank):
         e2e_value = world * 1000.0 / (ms_e2e / args.steps)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rate, desc, sample_bytes = cpu_oracle_rate(8)
+            rate, desc, sample_bytes = cpu_oracle_rate(args.config, 3)
             scaled = rate * sample_bytes / total_bytes
             cpu = {"value": scaled, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                    "sample": desc + f"; scaled by algorithmic bytes ({sample_bytes / total_bytes:.3e}) to this workload",
