@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RDG_ABI_VERSION 6
+#define RDG_ABI_VERSION 7
 #define RDG_TILE 16
 #define RDG_NUM_BASIS_MAX 16
 
@@ -119,12 +119,17 @@ typedef struct RdgBins {
     uint32_t* num_rendered;  /* [2]: [0] = D (sum tiles_touched), [1] = 1 if D > D_cap (nothing past D_cap is written) */
     uint64_t* keys_unsorted; /* optional [D_cap] for tests; NULL to use workspace */
     uint32_t* vals_unsorted; /* optional [D_cap] */
-    uint16_t* sub_masks;     /* optional [D_cap]: rdg_blend_fwd stores, per sorted instance, the 16-bit mask of the
-                              * 4x4-pixel sub-tiles the Gaussian can reach; rdg_blend_bwd reads it back (NULL:
-                              * the backward pass recomputes it) */
-    uint32_t* tile_order;    /* optional [tiles]: rdg_bin_tiles writes the tile ids by descending list length; the blend
-                              * kernels then launch their CTAs in that order (longest tiles first).  NULL: row-major
-                              * order.  rdg_bin does not write it - pass NULL with that path. */
+    /* Region lists, written by rdg_blend_fwd and read back by rdg_blend_bwd (required by both).  A region is a 16x8-pixel
+     * half tile (the unit one warp blends); region r of tile t holds, in depth order, the entries of the tile's list
+     * whose alpha >= 1/255 ellipse can reach it, with the 8-bit mask of the 4x4-pixel sub-tiles it reaches:
+     *   region_ids  [2 * region_stride]  entry k of region (t, r) at r * region_stride + ranges[t][0] + k
+     *   region_masks[2 * region_stride]  same indexing
+     *   region_count[2 * tiles]          entries of region (t, r) at 2 t + r
+     * region_stride >= D_cap.  RdgImage.n_contrib counts positions of the REGION list. */
+    uint32_t* region_ids;
+    uint8_t* region_masks;
+    uint32_t* region_count;
+    int64_t region_stride;
 } RdgBins;
 
 typedef struct RdgImage {
@@ -189,7 +194,8 @@ int rdg_bin_tiles(int64_t n, const RdgGeom* geom, int32_t height, int32_t width,
 int rdg_bin(int64_t n, const RdgGeom* geom, int32_t height, int32_t width, int64_t d_cap,
             const RdgBins* bins, void* workspace, int64_t workspace_bytes, void* stream);
 
-/* front-to-back alpha blend of colour, depth and alpha (§8 a9). */
+/* front-to-back alpha blend of colour, depth and alpha (§8 a9).  Two launches: the region lists (bins->region_*), then
+ * the blend itself. */
 int rdg_blend_fwd(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view,
                   const RdgImage* out, void* stream);
 

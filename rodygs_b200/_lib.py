@@ -43,7 +43,8 @@ class RdgGeom(C.Structure):
 
 class RdgBins(C.Structure):
     _fields_ = [("keys_sorted", c_ptr), ("vals_sorted", c_ptr), ("ranges", c_ptr), ("point_offsets", c_ptr),
-                ("num_rendered", c_ptr), ("keys_unsorted", c_ptr), ("vals_unsorted", c_ptr), ("sub_masks", c_ptr), ("tile_order", c_ptr)]
+                ("num_rendered", c_ptr), ("keys_unsorted", c_ptr), ("vals_unsorted", c_ptr), ("region_ids", c_ptr), ("region_masks", c_ptr),
+                ("region_count", c_ptr), ("region_stride", C.c_int64)]
 
 
 class RdgImage(C.Structure):
@@ -165,7 +166,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.rdg_abi_version() != 6:
+    if lib.rdg_abi_version() != 7:
         raise RuntimeError("librodygs_b200.so ABI version mismatch")
     _lib = lib
     return lib

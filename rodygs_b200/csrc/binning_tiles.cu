@@ -34,9 +34,8 @@
 // ------------------------------------------------------------ tile segments ----
 __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restrict__ tile_count, int tiles,
                                                          uint32_t* __restrict__ tile_off, uint32_t* __restrict__ num_rendered,
-                                                         uint32_t cap, uint32_t* __restrict__ tile_order) {
+                                                         uint32_t cap) {
     __shared__ uint32_t ws[33];
-    __shared__ uint32_t hist[1024];
     __shared__ uint32_t carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
@@ -74,44 +73,6 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
         tile_off[tiles] = carry_s;
         num_rendered[0] = carry_s;
         num_rendered[1] = carry_s > cap ? 1u : 0u;
-    }
-    // Launch order of the blend CTAs: longest lists first (LPT), so that the last wave of the 8160-CTA blend grids is made
-    // of the cheapest tiles instead of whatever sits in the bottom-right corner of the image.  Counting sort on
-    // count / 16 (1024 buckets, bucket 0 = longest); the order inside a bucket is arbitrary.
-    if (tile_order) {
-        hist[threadIdx.x] = 0;
-        __syncthreads();
-        for (int i = threadIdx.x; i < tiles; i += 1024) {
-            const uint32_t b = 1023u - min(tile_count[i] >> 4, 1023u);
-            atomicAdd(&hist[b], 1u);
-        }
-        __syncthreads();
-        const uint32_t mine = hist[threadIdx.x];
-        uint32_t v = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v += t;
-        }
-        if (lane == 31) ws[w] = v;
-        __syncthreads();
-        if (w == 0) {
-            const uint32_t x = ws[lane];
-            uint32_t y = x;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, y, o);
-                if (lane >= o) y += t;
-            }
-            ws[lane] = y - x;
-        }
-        __syncthreads();
-        hist[threadIdx.x] = ws[w] + v - mine;      // exclusive start of this bucket
-        __syncthreads();
-        for (int i = threadIdx.x; i < tiles; i += 1024) {
-            const uint32_t b = 1023u - min(tile_count[i] >> 4, 1023u);
-            tile_order[atomicAdd(&hist[b], 1u)] = (uint32_t)i;
-        }
     }
 }
 
@@ -392,8 +353,7 @@ extern "C" int rdg_bin_tiles(int64_t n, const RdgGeom* geom, int32_t height, int
     uint64_t* pairs_tmp = (uint64_t*)(ws + L.pairs_tmp);
     const int gx = (width + RDG_TILE - 1) / RDG_TILE, gy = (height + RDG_TILE - 1) / RDG_TILE;
     RDG_CUDA(cudaMemsetAsync(tile_fill, 0, (size_t)L.tiles * TP_FILL_STRIDE * sizeof(uint32_t), s));
-    tile_scan_kernel<<<1, 1024, 0, s>>>(geom->tile_count, L.tiles, tile_off, bins->num_rendered, (uint32_t)d_cap,
-                                        bins->tile_order);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(geom->tile_count, L.tiles, tile_off, bins->num_rendered, (uint32_t)d_cap);
     {
         const int64_t groups = (n + 31) / 32;
         const int64_t want = (groups + RDG_BLOCK / 32 - 1) / (RDG_BLOCK / 32);

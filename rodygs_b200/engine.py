@@ -45,10 +45,6 @@ class Config:
     #          emission-order arrays (point_offsets, unsorted keys/values) that the tests pin.
     binning: str = "tiles"
     emit_sorted_keys: bool = True       # write the sorted 64-bit keys (only verification reads them)
-    # launch the blend CTAs by descending tile list length (RdgBins.tile_order).  Off by default: measured on B200 at C4 the
-    # longest-first order is 2 % SLOWER in blend_bwd (1.282 vs 1.253 ms, profiles/r01_ab_v12_*.json) - row-major neighbours
-    # share Gaussians in L2, and that is worth more than a shorter last wave.  RDG_TILE_ORDER=1 turns it on.
-    tile_order: bool = os.environ.get("RDG_TILE_ORDER", "0") == "1"
 
 
 config = Config()
@@ -281,15 +277,17 @@ def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = T
         want_keys = config.emit_sorted_keys or not use_tiles
         keys = torch.empty(d_cap, dtype=torch.int64, device=dev) if want_keys else None
         vals = torch.empty(d_cap, dtype=torch.int32, device=dev)
-        sub_masks = torch.empty(d_cap, dtype=torch.int16, device=dev) if keep_for_backward else None
+        # region lists of the blend kernels (two 16x8 regions per tile; rdg_blend_fwd writes, rdg_blend_bwd reads)
+        region_ids = torch.empty(2 * d_cap, dtype=torch.int32, device=dev)
+        region_masks = torch.empty(2 * d_cap, dtype=torch.uint8, device=dev)
+        region_count = torch.empty(2 * ntiles, dtype=torch.int32, device=dev)
         ws_bytes = int((lib.rdg_bin_tiles_workspace_bytes if use_tiles else lib.rdg_bin_workspace_bytes)(n, d_cap, H, W))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         bins = RdgBins()
         bins.keys_sorted, bins.vals_sorted = ptr(keys), ptr(vals)
         bins.ranges, bins.point_offsets, bins.num_rendered = ptr(ranges), ptr(point_offsets), ptr(num_rendered)
-        bins.sub_masks = ptr(sub_masks)
-        tile_order = torch.empty(ntiles, dtype=torch.int32, device=dev) if (use_tiles and config.tile_order) else None
-        bins.tile_order = ptr(tile_order)
+        bins.region_ids, bins.region_masks, bins.region_count = ptr(region_ids), ptr(region_masks), ptr(region_count)
+        bins.region_stride = d_cap
         if config.debug_keep_unsorted:
             extras["keys_unsorted"] = torch.empty(d_cap, dtype=torch.int64, device=dev)
             extras["vals_unsorted"] = torch.empty(d_cap, dtype=torch.int32, device=dev)
@@ -323,7 +321,8 @@ def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = T
     if stage_hook:
         stage_hook("blend_fwd")
 
-    extras.update({"keys_sorted": keys, "point_offsets": point_offsets, "sub_masks": sub_masks, "tile_order": tile_order})
+    extras.update({"keys_sorted": keys, "point_offsets": point_offsets, "region_ids": region_ids, "region_masks": region_masks,
+                   "region_count": region_count})
     state = FwdState(scene=scene, view=view, n=n, geom=geom, vals_sorted=vals, ranges=ranges,
                      num_rendered=num_rendered, final_T=final_T, n_contrib=n_contrib, d_cap=d_cap, extras=extras)
     return color, depth, alpha, geom["radii"], state
@@ -375,8 +374,8 @@ def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: Sce
     sc_s, vw_s, gm_s = _scene_struct(state.scene), _view_struct(state.view), _geom_struct(state.geom)
     bins = RdgBins()
     bins.vals_sorted, bins.ranges, bins.num_rendered = ptr(state.vals_sorted), ptr(state.ranges), ptr(state.num_rendered)
-    bins.sub_masks = ptr(state.extras.get("sub_masks"))
-    bins.tile_order = ptr(state.extras.get("tile_order"))
+    bins.region_ids, bins.region_masks = ptr(state.extras["region_ids"]), ptr(state.extras["region_masks"])
+    bins.region_count, bins.region_stride = ptr(state.extras["region_count"]), state.d_cap
     img = RdgImage()
     img.final_T, img.n_contrib = ptr(state.final_T), ptr(state.n_contrib)
 

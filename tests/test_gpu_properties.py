@@ -16,7 +16,6 @@ def _reset():
     engine.config.sync_free = False
     engine.config.debug_keep_unsorted = False
     engine.config.binning = "tiles"
-    engine.config.tile_order = False
 
 
 def _step(cfg, n_override=None):
@@ -38,7 +37,6 @@ def _forward(step, cam):
 @pytest.mark.parametrize("cfg,binning", [("c2_kubric", "tiles"), ("c2_kubric", "lsd"), ("c4_iphone", "tiles"), ("c4_iphone", "lsd")])
 def test_binning_tables_are_consistent_at_full_size(cfg, binning):
     engine.config.binning = binning
-    engine.config.tile_order = True      # optional longest-first launch order of the blend CTAs (off by default)
     step, cam, (N, H, W, T) = _step(cfg)
     (color, depth, alpha, radii), st = _forward(step, cam)
     D = int(st.num_rendered[0])
@@ -67,15 +65,6 @@ def test_binning_tables_are_consistent_at_full_size(cfg, binning):
     assert torch.equal(torch.bincount(tile_of, minlength=gx * gy), ranges[:, 1] - ranges[:, 0])
     starts = ranges[ne, 0]
     assert torch.equal(tile_of[starts], torch.nonzero(ne).squeeze(1))
-    # launch order of the blend CTAs: a permutation of the tiles, longest lists first (16-entry granularity)
-    order = st.extras.get("tile_order")
-    if binning == "tiles":
-        assert order is not None
-        assert torch.equal(torch.sort(order.long()).values, torch.arange(gx * gy, device=order.device))
-        level = torch.clamp((ranges[:, 1] - ranges[:, 0]) >> 4, max=1023)[order.long()]
-        assert bool((level[1:] <= level[:-1]).all()), "tile order is not descending in list length"
-    else:
-        assert order is None
     # stable order: inside a tile, equal depth bits keep ascending Gaussian index
     same = (keys[1:] == keys[:-1])
     assert bool((vals[1:][same] > vals[:-1][same]).all())
