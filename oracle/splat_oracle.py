@@ -24,7 +24,13 @@ Backward is PyTorch autograd over this forward, with the upstream
 conventions of SURVEY.md App. A.6 written in explicitly:
 (i) straight-through ``min(0.99, .)``; (ii) skip rules are constants;
 (iii) SH clamp zeroes the gradient; (iv) the +-1.3 tan(fov) clamp freezes the
-clamped coordinate; (vi) no quaternion-normalisation Jacobian.
+clamped coordinate; (v) the cov2D-inverse backward divides by ``det^2 + 1e-7``
+(``_ConicFromCov``); (vi) no quaternion-normalisation Jacobian.
+
+The outputs of this file on a fixed scene are frozen in
+``tests/golden/raster_small.npz`` (``tests/golden/make_golden_raster.py``), and
+``oracle/splat_scalar.py`` is a second, independently structured restatement
+(scalar loops) that ``tests/test_oracle_scalar.py`` checks this one against.
 """
 from __future__ import annotations
 
@@ -115,6 +121,26 @@ def sh_grad_from_factors(deg: int, means_per_view, campos_per_view, dcolor_per_v
         d = d / d.norm(dim=1, keepdim=True)
         g[:, :K] += sh_basis(deg, d).unsqueeze(2) * dc.unsqueeze(1)
     return g
+
+
+class _ConicFromCov(torch.autograd.Function):
+    """conic = cov2D^-1 = (c, -b, a) / det.  Forward exactly as App. A.2 step 5; backward as App. A.6 (v): the public
+    implementation differentiates the inverse with ``1 / (det^2 + 1e-7)`` in place of ``1 / det^2`` (the B gradient is
+    that of the single stored off-diagonal, which appears once in ``power``)."""
+
+    @staticmethod
+    def forward(ctx, ca, cb, cc, det, det_inv):
+        ctx.save_for_backward(ca, cb, cc, det)
+        return cc * det_inv, -cb * det_inv, ca * det_inv
+
+    @staticmethod
+    def backward(ctx, gA, gB, gC):
+        ca, cb, cc, det = ctx.saved_tensors
+        d2 = 1.0 / (det * det + 1e-7)
+        da = d2 * (-cc * cc * gA + cb * cc * gB - cb * cb * gC)
+        db = d2 * (2.0 * cb * cc * gA - (det + 2.0 * cb * cb) * gB + 2.0 * ca * cb * gC)
+        dc = d2 * (-cb * cb * gA + ca * cb * gB - ca * ca * gC)
+        return da, db, dc, None, None
 
 
 class Preprocessed(NamedTuple):
@@ -245,9 +271,7 @@ def preprocess(means3D, scales, rotations, opacities, shs, colors_precomp,
     det_ok = det.detach() != 0
     det_safe = torch.where(det_ok, det, torch.ones_like(det))
     det_inv = one / det_safe
-    conA = cc * det_inv
-    conB = -cb * det_inv
-    conC = ca * det_inv
+    conA, conB, conC = _ConicFromCov.apply(ca, cb, cc, det_safe.detach(), det_inv.detach())
 
     # -- 6./7./8. radius, pixel centre, tile rectangle (integer outputs) --------
     with torch.no_grad():

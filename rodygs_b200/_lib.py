@@ -157,11 +157,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("RDG_LIB_PATH", LIB_PATH)   # development: an A/B build of the same sources (tools/build_variant.py)
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing. Build it with `python -m rodygs_b200.build` (needs nvcc); "
+            f"{path} is missing. Build it with `python -m rodygs_b200.build` (needs nvcc); "
             "rodygs_b200 has no CPU or PyTorch fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res

@@ -35,15 +35,27 @@
 
 #define RSUBS 8                 // 4x4-pixel sub-tiles per region (= lane groups of 4 per warp)
 #define REGIONS 2               // regions (16x8 half tiles) per tile
-#define CH 64                   // region-list entries staged per chunk (two per lane)
+#ifndef CH
+#define CH 64                   // region-list entries staged per chunk (up to two per lane; 32 < CH <= 64)
+#endif
 #define NSLOT (CH + 1)          // + the null slot (opacity 0) that pads the lists
-#define LROW (CH + 2)           // list row stride (u16)
+#define LROW (CH + 4)           // list row stride (u16): CH entries + the two null entries the record prefetch may touch
+#ifndef POOL
 #define POOL 192                // (sub-tile, entry) gradient records per chunk (backward); 64 entries average 154
+#endif
+#ifndef FWD_MINB
+#define FWD_MINB 12             // __launch_bounds__ minimum CTAs per SM, forward / backward
+#endif
+#ifndef BWD_MINB
+#define BWD_MINB 8
+#endif
 #define PREC 10                 // floats per record (40-byte rows)
 #define RDG_PW_FLAG 0x80000000u // region-list id bit: this entry's power may round to a positive value, test it
 #define NULL_ENTRY ((uint16_t)(CH | (POOL << 7)))   // list entry = slot | record index << 7; null: slot CH, scratch record POOL
 #define FULL 0xffffffffu
-#define BLEND_WARPS 2           // warps per CTA = regions of one tile
+#ifndef BLEND_WARPS
+#define BLEND_WARPS 2           // warps per CTA; every warp blends one region on its own (no block-level synchronisation)
+#endif
 
 int rdg_blend_fwd_r1(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view, const RdgImage* out, void* stream);
 int rdg_blend_bwd_r1(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view, const RdgImage* fwd,
@@ -248,7 +260,7 @@ __device__ __forceinline__ int rdg_compact8(StagedW& sm, unsigned m_lo, unsigned
         my_n = (s == my_s) ? n_s : my_n;
     }
     uint16_t* row = sm.list[my_s];
-    for (int k = my_n + (lane & 3); k < nmax; k += 4) row[k] = NULL_ENTRY;
+    for (int k = my_n + (lane & 3); k < nmax + 2; k += 4) row[k] = NULL_ENTRY;   // + 2: the loops fetch the record one entry ahead
     __syncwarp();
     return nmax;
 }
@@ -283,13 +295,15 @@ __device__ __forceinline__ unsigned rdg_groups_of(unsigned act) {
 }
 
 struct BlendGeo {
-    int tile, region, tx, ty, lane, s, x, pxi, py0;
+    int tile, region, warp, tx, ty, lane, s, x, pxi, py0;
     bool in[4];
 };
 __device__ __forceinline__ BlendGeo rdg_geo(int gx, int W, int H) {
     BlendGeo g;
-    g.tile = blockIdx.x;
-    g.region = threadIdx.x >> 5;
+    g.warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * BLEND_WARPS + g.warp;              // region index: 2 * tile + half
+    g.tile = gw >> 1;
+    g.region = gw & 1;
     g.lane = threadIdx.x & 31;
     g.tx = g.tile % gx;
     g.ty = g.tile / gx;
@@ -360,15 +374,17 @@ __device__ __forceinline__ void rdg_fwd_pair(FwdPair& p, float Adx2, float Bdx, 
 #define RDG_NAN_POS 0x7fc00000u      // quiet NaN; the low 22 bits carry a list position
 __device__ __forceinline__ bool rdg_finished(float thr) { return thr != thr; }
 
-__global__ void __launch_bounds__(32 * BLEND_WARPS, 12) blend_fwd_kernel(
+__global__ void __launch_bounds__(32 * BLEND_WARPS, FWD_MINB) blend_fwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ rl_ids, const uint8_t* __restrict__ rl_masks, int64_t stride,
     const uint32_t* __restrict__ rcount, const float4* __restrict__ p0, const float4* __restrict__ p1,
-    const float2* __restrict__ p2, const float* __restrict__ bg, int W, int H, int gx, float* __restrict__ out_color,
+    const float2* __restrict__ p2, const float* __restrict__ bg, int W, int H, int gx, int n_tiles, float* __restrict__ out_color,
     float* __restrict__ out_depth, float* __restrict__ out_alpha, float* __restrict__ out_T, uint32_t* __restrict__ out_ncontrib) {
     __shared__ StagedW sm_all[BLEND_WARPS];
     const BlendGeo geo = rdg_geo(gx, W, H);
-    StagedW& sm = sm_all[geo.region];
+    if (geo.tile >= n_tiles) return;
+    StagedW& sm = sm_all[geo.warp];
     const int lane = geo.lane;
+    const bool hi_ok = lane + 32 < CH;                            // slot lane + 32 exists
     const float pixx = (float)geo.pxi;
     const int n_g = (int)rcount[REGIONS * geo.tile + geo.region];
     const size_t lbase = (size_t)geo.region * stride + ranges[geo.tile].x;
@@ -391,11 +407,11 @@ __global__ void __launch_bounds__(32 * BLEND_WARPS, 12) blend_fwd_kernel(
     // chunk 0 in flight; ids / masks of chunk 1 in registers
     uint32_t id_lo = 0, id_hi = 0, mk_lo = 0, mk_hi = 0;
     if (lane < n_g) { id_lo = ids[lane]; mk_lo = masks[lane]; rdg_issue(sa, sb, sc, 0, lane, id_lo, p0, p1, p2); }
-    if (lane + 32 < n_g) { id_hi = ids[lane + 32]; mk_hi = masks[lane + 32]; rdg_issue(sa, sb, sc, 0, lane + 32, id_hi, p0, p1, p2); }
+    if (hi_ok && lane + 32 < n_g) { id_hi = ids[lane + 32]; mk_hi = masks[lane + 32]; rdg_issue(sa, sb, sc, 0, lane + 32, id_hi, p0, p1, p2); }
     rdg_cp_commit();
     uint32_t idn_lo = 0, idn_hi = 0, mkn_lo = 0, mkn_hi = 0;
     if (CH + lane < n_g) { idn_lo = ids[CH + lane]; mkn_lo = masks[CH + lane]; }
-    if (CH + lane + 32 < n_g) { idn_hi = ids[CH + lane + 32]; mkn_hi = masks[CH + lane + 32]; }
+    if (hi_ok && CH + lane + 32 < n_g) { idn_hi = ids[CH + lane + 32]; mkn_hi = masks[CH + lane + 32]; }
 
     int buf = 0;
     for (int base = 0; base < n_g; base += CH, buf ^= 1) {
@@ -408,30 +424,32 @@ __global__ void __launch_bounds__(32 * BLEND_WARPS, 12) blend_fwd_kernel(
         const bool test_pw = __any_sync(FULL, ((id_lo | id_hi) & RDG_PW_FLAG) != 0u);
         // next chunk's copies fly during the blend
         if (base + CH + lane < n_g) rdg_issue(sa, sb, sc, buf ^ 1, lane, idn_lo, p0, p1, p2);
-        if (base + CH + lane + 32 < n_g) rdg_issue(sa, sb, sc, buf ^ 1, lane + 32, idn_hi, p0, p1, p2);
+        if (hi_ok && base + CH + lane + 32 < n_g) rdg_issue(sa, sb, sc, buf ^ 1, lane + 32, idn_hi, p0, p1, p2);
         rdg_cp_commit();
         mk_lo = mkn_lo; mk_hi = mkn_hi; id_lo = idn_lo; id_hi = idn_hi;
         mkn_lo = mkn_hi = idn_lo = idn_hi = 0u;
         if (base + 2 * CH + lane < n_g) { idn_lo = ids[base + 2 * CH + lane]; mkn_lo = masks[base + 2 * CH + lane]; }
-        if (base + 2 * CH + lane + 32 < n_g) { idn_hi = ids[base + 2 * CH + lane + 32]; mkn_hi = masks[base + 2 * CH + lane + 32]; }
+        if (hi_ok && base + 2 * CH + lane + 32 < n_g) { idn_hi = ids[base + 2 * CH + lane + 32]; mkn_hi = masks[base + 2 * CH + lane + 32]; }
 
         const int nmax = rdg_compact8<false>(sm, m_lo, m_hi, lane);
         const uint32_t boff = (uint32_t)(buf * NSLOT) * 16u;
         auto blend_lists = [&](auto pw_tag) {
             constexpr bool PW = decltype(pw_tag)::value;
-            uint32_t j_next = rdg_lds16(my_list);
+            // software pipeline: the record of entry i + 1 is requested before entry i is blended (rows are padded with nulls)
+            uint32_t j = rdg_lds16(my_list) & 0x7fu, j_next = rdg_lds16(my_list + 2u) & 0x7fu;
+            float4 a = rdg_lds128(sa + boff + (j << 4)), b = rdg_lds128(sb + boff + (j << 4));
+            float2 c = rdg_lds64(sc + ((boff + (j << 4)) >> 1));
             for (int i = 0; i < nmax; ++i) {
-                const uint32_t j = j_next & 0x7fu;
-                j_next = rdg_lds16(my_list + 2u * (i + 1));        // one entry ahead (rows are padded): off the critical path
-                const uint32_t o16 = boff + (j << 4);
-                const float4 a = rdg_lds128(sa + o16);
-                const float4 b = rdg_lds128(sb + o16);
-                const float2 c = rdg_lds64(sc + (o16 >> 1));
+                const uint32_t o16n = boff + (j_next << 4);
+                const float4 a_n = rdg_lds128(sa + o16n), b_n = rdg_lds128(sb + o16n);
+                const float2 c_n = rdg_lds64(sc + (o16n >> 1));
+                const uint32_t j_nn = rdg_lds16(my_list + 2u * (i + 2)) & 0x7fu;
                 const float dx = a.x - pixx;
                 const float Adx2 = (a.z * dx) * dx, Bdx = a.w * dx;
                 const float nanpos = __uint_as_float(((uint32_t)base + j) | RDG_NAN_POS);   // position of this entry, should a pixel stop at it
                 rdg_fwd_pair<PW>(pa, Adx2, Bdx, b, c, a.y, nanpos);
                 rdg_fwd_pair<PW>(pb, Adx2, Bdx, b, c, a.y, nanpos);
+                a = a_n; b = b_n; c = c_n; j = j_next; j_next = j_nn;
             }
         };
         if (test_pw) blend_lists(std::true_type{});
@@ -531,45 +549,59 @@ __device__ __forceinline__ float rdg_bwd_rules(float pw, float oG, uint32_t pos,
     return r;
 }
 
-// One entry on one pair: advances T and A_dot, returns w = dL/dG * G (per pixel), the blend weight alpha T and dy.
-// A pixel that skips the entry (rule or position) gets o G := 0, which makes alpha = 0, 1 / (1 - alpha) = 1 (exactly:
-// rcp.approx(1) = 1), w = 0 and leaves T and A_dot untouched - one select instead of masking every product.
+// One entry on the lane's four pixels (two pairs): advances T and A_dot, returns per pair w = dL/dG * G, the blend weight
+// alpha T and dy.  A pixel that skips the entry (rule or position) gets o G := 0, which makes alpha = 0, 1 / (1 - alpha)
+// = 1 (exactly: rcp.approx(1) = 1), w = 0 and leaves T and A_dot untouched - one select instead of masking every product.
+// The two pairs go through the stages side by side so that their MUFU / select chains overlap.
 template <bool POS, bool PW>
-__device__ __forceinline__ void rdg_bwd_pair(BwdPair& p, float Adx2, float Bdx, const float4& b, const float2& c, float py, uint32_t pos,
-                                             f2_t& w2, f2_t& wgt2, f2_t& dy2) {
-    f2_t power;
-    const f2_t og = rdg_og2(Adx2, Bdx, b.x, py, b.y, p.npixy, power, dy2);
-    float pw0, pw1, oG0, oG1;
-    rdg_unpk(power, pw0, pw1);
-    rdg_unpk(og, oG0, oG1);
-    oG0 = rdg_bwd_rules<POS, PW>(pw0, oG0, pos, p.last0);
-    oG1 = rdg_bwd_rules<POS, PW>(pw1, oG1, pos, p.last1);
-    const f2_t al2 = rdg_pk(fminf(RDG_ALPHA_MAX, oG0), fminf(RDG_ALPHA_MAX, oG1));
-    float om0, om1;
-    rdg_unpk(rdg_fma2(al2, rdg_bc(-1.0f), rdg_bc(1.0f)), om0, om1);
-    const f2_t inv2 = rdg_pk(rdg_rcp(om0), rdg_rcp(om1));
-    p.T = rdg_mul2(p.T, inv2);                                     // transmittance in front of this Gaussian
-    wgt2 = rdg_mul2(al2, p.T);
-    const f2_t P2 = rdg_fma2(rdg_bc(b.z), p.gr, rdg_fma2(rdg_bc(b.w), p.gg, rdg_fma2(rdg_bc(c.x), p.gb, rdg_fma2(rdg_bc(c.y), p.gd, p.ga))));
-    float nia0, nia1;
-    rdg_unpk(rdg_mul2(inv2, p.A), nia0, nia1);
-    const f2_t dLda2 = rdg_fma2(p.T, P2, rdg_pk(-nia0, -nia1));
-    p.A = rdg_fma2(P2, wgt2, p.A);
-    w2 = rdg_mul2(rdg_pk(oG0, oG1), dLda2);                        // straight-through clamp: o G, not alpha (App. A.6 i)
+__device__ __forceinline__ void rdg_bwd_quad(BwdPair& pa, BwdPair& pb, float Adx2, float Bdx, const float4& b, const float2& c, float py,
+                                             uint32_t pos, f2_t& wa, f2_t& wb, f2_t& wga, f2_t& wgb, f2_t& dya, f2_t& dyb) {
+    f2_t pwa, pwb;
+    const f2_t oga = rdg_og2(Adx2, Bdx, b.x, py, b.y, pa.npixy, pwa, dya);
+    const f2_t ogb = rdg_og2(Adx2, Bdx, b.x, py, b.y, pb.npixy, pwb, dyb);
+    const f2_t Pa = rdg_fma2(rdg_bc(b.z), pa.gr, rdg_fma2(rdg_bc(b.w), pa.gg, rdg_fma2(rdg_bc(c.x), pa.gb, rdg_fma2(rdg_bc(c.y), pa.gd, pa.ga))));
+    const f2_t Pb = rdg_fma2(rdg_bc(b.z), pb.gr, rdg_fma2(rdg_bc(b.w), pb.gg, rdg_fma2(rdg_bc(c.x), pb.gb, rdg_fma2(rdg_bc(c.y), pb.gd, pb.ga))));
+    float pw[4], oG[4];
+    rdg_unpk(pwa, pw[0], pw[1]); rdg_unpk(pwb, pw[2], pw[3]);
+    rdg_unpk(oga, oG[0], oG[1]); rdg_unpk(ogb, oG[2], oG[3]);
+    oG[0] = rdg_bwd_rules<POS, PW>(pw[0], oG[0], pos, pa.last0);
+    oG[1] = rdg_bwd_rules<POS, PW>(pw[1], oG[1], pos, pa.last1);
+    oG[2] = rdg_bwd_rules<POS, PW>(pw[2], oG[2], pos, pb.last0);
+    oG[3] = rdg_bwd_rules<POS, PW>(pw[3], oG[3], pos, pb.last1);
+    const f2_t ala = rdg_pk(fminf(RDG_ALPHA_MAX, oG[0]), fminf(RDG_ALPHA_MAX, oG[1]));
+    const f2_t alb = rdg_pk(fminf(RDG_ALPHA_MAX, oG[2]), fminf(RDG_ALPHA_MAX, oG[3]));
+    float om[4];
+    rdg_unpk(rdg_fma2(ala, rdg_bc(-1.0f), rdg_bc(1.0f)), om[0], om[1]);
+    rdg_unpk(rdg_fma2(alb, rdg_bc(-1.0f), rdg_bc(1.0f)), om[2], om[3]);
+    const f2_t inva = rdg_pk(rdg_rcp(om[0]), rdg_rcp(om[1])), invb = rdg_pk(rdg_rcp(om[2]), rdg_rcp(om[3]));
+    pa.T = rdg_mul2(pa.T, inva);                                   // transmittance in front of this Gaussian
+    pb.T = rdg_mul2(pb.T, invb);
+    wga = rdg_mul2(ala, pa.T);
+    wgb = rdg_mul2(alb, pb.T);
+    float nia[4];
+    rdg_unpk(rdg_mul2(inva, pa.A), nia[0], nia[1]);
+    rdg_unpk(rdg_mul2(invb, pb.A), nia[2], nia[3]);
+    const f2_t dLa = rdg_fma2(pa.T, Pa, rdg_pk(-nia[0], -nia[1])), dLb = rdg_fma2(pb.T, Pb, rdg_pk(-nia[2], -nia[3]));
+    pa.A = rdg_fma2(Pa, wga, pa.A);
+    pb.A = rdg_fma2(Pb, wgb, pb.A);
+    wa = rdg_mul2(rdg_pk(oG[0], oG[1]), dLa);                      // straight-through clamp: o G, not alpha (App. A.6 i)
+    wb = rdg_mul2(rdg_pk(oG[2], oG[3]), dLb);
 }
 
-__global__ void __launch_bounds__(32 * BLEND_WARPS, 9) blend_bwd_kernel(
+__global__ void __launch_bounds__(32 * BLEND_WARPS, BWD_MINB) blend_bwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ rl_ids, const uint8_t* __restrict__ rl_masks, int64_t stride,
     const uint32_t* __restrict__ rcount, const float4* __restrict__ p0, const float4* __restrict__ p1,
-    const float2* __restrict__ p2, const float* __restrict__ bg, int W, int H, int gx, const float* __restrict__ final_T,
+    const float2* __restrict__ p2, const float* __restrict__ bg, int W, int H, int gx, int n_tiles, const float* __restrict__ final_T,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
     const float* __restrict__ dL_dalpha, float* __restrict__ acc) {
     __shared__ StagedW sm_all[BLEND_WARPS];
     __shared__ __align__(16) float pool_all[BLEND_WARPS][(POOL + 1) * PREC];   // + the scratch record of the null entry
     const BlendGeo geo = rdg_geo(gx, W, H);
-    StagedW& sm = sm_all[geo.region];
-    float* pool = pool_all[geo.region];
+    if (geo.tile >= n_tiles) return;
+    StagedW& sm = sm_all[geo.warp];
+    float* pool = pool_all[geo.warp];
     const int lane = geo.lane;
+    const bool hi_ok = lane + 32 < CH;                            // slot lane + 32 exists
     const float pixx = (float)geo.pxi;
     const int n_g = (int)rcount[REGIONS * geo.tile + geo.region];
     const size_t lbase = (size_t)geo.region * stride + ranges[geo.tile].x;
@@ -642,11 +674,11 @@ __global__ void __launch_bounds__(32 * BLEND_WARPS, 9) blend_bwd_kernel(
     int done_slots = 0, buf = 0, pf_start = 0;
     uint32_t idc_lo = 0, idc_hi = 0, mkc_lo = 0, mkc_hi = 0;       // this round's entries
     if (lane < n_l) { idc_lo = ids[n_l - 1 - lane]; mkc_lo = masks[n_l - 1 - lane]; rdg_issue(sa, sb, sc, 0, lane, idc_lo, p0, p1, p2); }
-    if (lane + 32 < n_l) { idc_hi = ids[n_l - 33 - lane]; mkc_hi = masks[n_l - 33 - lane]; rdg_issue(sa, sb, sc, 0, lane + 32, idc_hi, p0, p1, p2); }
+    if (hi_ok && lane + 32 < n_l) { idc_hi = ids[n_l - 33 - lane]; mkc_hi = masks[n_l - 33 - lane]; rdg_issue(sa, sb, sc, 0, lane + 32, idc_hi, p0, p1, p2); }
     rdg_cp_commit();
     uint32_t idn_lo = 0, idn_hi = 0, mkn_lo = 0, mkn_hi = 0;       // the next round's, assuming no cut
     if (CH + lane < n_l) { idn_lo = ids[n_l - 1 - CH - lane]; mkn_lo = masks[n_l - 1 - CH - lane]; }
-    if (CH + lane + 32 < n_l) { idn_hi = ids[n_l - 33 - CH - lane]; mkn_hi = masks[n_l - 33 - CH - lane]; }
+    if (hi_ok && CH + lane + 32 < n_l) { idn_hi = ids[n_l - 33 - CH - lane]; mkn_hi = masks[n_l - 33 - CH - lane]; }
 
     while (done_slots < n_l) {
         const int cnt = min(CH, n_l - done_slots);
@@ -654,16 +686,16 @@ __global__ void __launch_bounds__(32 * BLEND_WARPS, 9) blend_bwd_kernel(
         if (pf_start != done_slots) {                              // the previous round was cut short (uniform branch)
             idc_lo = idc_hi = mkc_lo = mkc_hi = 0u;
             if (lane < cnt) { idc_lo = ids[pos0 - lane]; mkc_lo = masks[pos0 - lane]; rdg_issue(sa, sb, sc, buf, lane, idc_lo, p0, p1, p2); }
-            if (lane + 32 < cnt) { idc_hi = ids[pos0 - 32 - lane]; mkc_hi = masks[pos0 - 32 - lane]; rdg_issue(sa, sb, sc, buf, lane + 32, idc_hi, p0, p1, p2); }
+            if (hi_ok && lane + 32 < cnt) { idc_hi = ids[pos0 - 32 - lane]; mkc_hi = masks[pos0 - 32 - lane]; rdg_issue(sa, sb, sc, buf, lane + 32, idc_hi, p0, p1, p2); }
             rdg_cp_commit();
             pf_start = done_slots;
             idn_lo = idn_hi = mkn_lo = mkn_hi = 0u;
             if (CH + lane < n_l - done_slots) { idn_lo = ids[pos0 - CH - lane]; mkn_lo = masks[pos0 - CH - lane]; }
-            if (CH + lane + 32 < n_l - done_slots) { idn_hi = ids[pos0 - CH - 32 - lane]; mkn_hi = masks[pos0 - CH - 32 - lane]; }
+            if (hi_ok && CH + lane + 32 < n_l - done_slots) { idn_hi = ids[pos0 - CH - 32 - lane]; mkn_hi = masks[pos0 - CH - 32 - lane]; }
         }
         rdg_cp_wait_all();
         __syncwarp();                                              // copies visible; everybody is done with the previous flush
-        unsigned m_lo = lane < cnt ? mkc_lo : 0u, m_hi = lane + 32 < cnt ? mkc_hi : 0u;
+        unsigned m_lo = lane < cnt ? mkc_lo : 0u, m_hi = lane + 32 < cnt ? mkc_hi : 0u;   // (cnt <= CH)
         if ((uint32_t)pos0 >= min_qlast) {                         // some sub-tile stopped in front of this round (uniform branch)
             const uint32_t pos_lo = (uint32_t)(pos0 - lane), pos_hi = (uint32_t)(pos0 - 32 - lane);
 #pragma unroll
@@ -692,33 +724,33 @@ __global__ void __launch_bounds__(32 * BLEND_WARPS, 9) blend_bwd_kernel(
         const int cnt2 = __popc(__ballot_sync(FULL, keep_lo)) + __popc(__ballot_sync(FULL, keep_hi));   // keep is a prefix
         // next round's copies (assuming no cut) fly during the blend
         if (done_slots + CH + lane < n_l) rdg_issue(sa, sb, sc, buf ^ 1, lane, idn_lo, p0, p1, p2);
-        if (done_slots + CH + lane + 32 < n_l) rdg_issue(sa, sb, sc, buf ^ 1, lane + 32, idn_hi, p0, p1, p2);
+        if (hi_ok && done_slots + CH + lane + 32 < n_l) rdg_issue(sa, sb, sc, buf ^ 1, lane + 32, idn_hi, p0, p1, p2);
         rdg_cp_commit();
         const uint32_t idp_lo = idn_lo, idp_hi = idn_hi, mkp_lo = mkn_lo, mkp_hi = mkn_hi;
         idn_lo = idn_hi = mkn_lo = mkn_hi = 0u;
         if (done_slots + 2 * CH + lane < n_l) { idn_lo = ids[pos0 - 2 * CH - lane]; mkn_lo = masks[pos0 - 2 * CH - lane]; }
-        if (done_slots + 2 * CH + lane + 32 < n_l) { idn_hi = ids[pos0 - 2 * CH - 32 - lane]; mkn_hi = masks[pos0 - 2 * CH - 32 - lane]; }
+        if (hi_ok && done_slots + 2 * CH + lane + 32 < n_l) { idn_hi = ids[pos0 - 2 * CH - 32 - lane]; mkn_hi = masks[pos0 - 2 * CH - 32 - lane]; }
 
         const int nmax = rdg_compact8<true>(sm, m_lo, m_hi, lane, eb_lo, eb_hi);
         const uint32_t boff = (uint32_t)(buf * NSLOT) * 16u;
         auto blend_lists = [&](auto pos_tag, auto pw_tag) {
             constexpr bool POS = decltype(pos_tag)::value, PW = decltype(pw_tag)::value;
-            uint32_t ent_next = rdg_lds16(my_list);
+            // software pipeline: the record of entry i + 1 is requested before entry i is blended (rows are padded with nulls)
+            uint32_t ent = rdg_lds16(my_list), ent_next = rdg_lds16(my_list + 2u);
+            float4 a = rdg_lds128(sa + boff + ((ent & 0x7fu) << 4)), b = rdg_lds128(sb + boff + ((ent & 0x7fu) << 4));
+            float2 c = rdg_lds64(sc + ((boff + ((ent & 0x7fu) << 4)) >> 1));
             for (int i = 0; i < nmax; ++i) {
-                const uint32_t ent = ent_next;
-                ent_next = rdg_lds16(my_list + 2u * (i + 1));      // one entry ahead (rows are padded): off the critical path
+                const uint32_t o16n = boff + ((ent_next & 0x7fu) << 4);
+                const float4 a_n = rdg_lds128(sa + o16n), b_n = rdg_lds128(sb + o16n);
+                const float2 c_n = rdg_lds64(sc + (o16n >> 1));
+                const uint32_t ent_nn = rdg_lds16(my_list + 2u * (i + 2));
                 const uint32_t j = ent & 0x7fu;
-                const uint32_t o16 = boff + (j << 4);
-                const float4 a = rdg_lds128(sa + o16);
-                const float4 b = rdg_lds128(sb + o16);
-                const float2 c = rdg_lds64(sc + (o16 >> 1));
                 const uint32_t rec = (ent >> 7) * (uint32_t)(PREC * 4);
                 const uint32_t pos = (uint32_t)pos0 - j;           // null slot: garbage, but its alpha test fails
                 const float dx = a.x - pixx;
                 const float Adx2 = (a.z * dx) * dx, Bdx = a.w * dx;
                 f2_t wa, wb, wga, wgb, dya, dyb;
-                rdg_bwd_pair<POS, PW>(pa, Adx2, Bdx, b, c, a.y, pos, wa, wga, dya);
-                rdg_bwd_pair<POS, PW>(pb, Adx2, Bdx, b, c, a.y, pos, wb, wgb, dyb);
+                rdg_bwd_quad<POS, PW>(pa, pb, Adx2, Bdx, b, c, a.y, pos, wa, wb, wga, wgb, dya, dyb);
                 // raw moments about the Gaussian centre, pre-added over the column (dx is common to its four pixels);
                 // the conic / sign factors are applied once per (Gaussian, region) at the flush
                 const f2_t wya = rdg_mul2(wa, dya), wyb = rdg_mul2(wb, dyb);
@@ -737,6 +769,7 @@ __global__ void __launch_bounds__(32 * BLEND_WARPS, 9) blend_bwd_kernel(
                 rdg_reduce_q4(v, b1, b0, r0, r1, r2);
                 rdg_sts64(pool_mine + rec, r0, r1);
                 rdg_sts32_if(!b0, pool_third + rec, r2);
+                a = a_n; b = b_n; c = c_n; ent = ent_next; ent_next = ent_nn;
             }
         };
         // every position of this round lies below every n_contrib of the warp: no per-entry position test
@@ -800,9 +833,9 @@ extern "C" int rdg_blend_fwd(int64_t n, const RdgGeom* geom, const RdgBins* bins
     tile_split_kernel<<<gx * gy, 128, 0, s>>>((const uint2*)bins->ranges, bins->vals_sorted, (const float4*)geom->p0,
                                               (const float4*)geom->p1, gx, bins->region_ids, bins->region_masks,
                                               bins->region_stride, bins->region_count);
-    blend_fwd_kernel<<<gx * gy, 32 * BLEND_WARPS, 0, s>>>(
+    blend_fwd_kernel<<<(REGIONS * gx * gy + BLEND_WARPS - 1) / BLEND_WARPS, 32 * BLEND_WARPS, 0, s>>>(
         (const uint2*)bins->ranges, bins->region_ids, bins->region_masks, bins->region_stride, bins->region_count,
-        (const float4*)geom->p0, (const float4*)geom->p1, (const float2*)geom->p2, view->bg, W, H, gx, out->color, out->depth,
+        (const float4*)geom->p0, (const float4*)geom->p1, (const float2*)geom->p2, view->bg, W, H, gx, gx * gy, out->color, out->depth,
         out->alpha, out->final_T, out->n_contrib);
     RDG_CHECK_LAUNCH();
     rdg_count_launches(2);
@@ -818,9 +851,9 @@ extern "C" int rdg_blend_bwd(int64_t n, const RdgGeom* geom, const RdgBins* bins
     RDG_CHECK_ARG(bins->region_ids && bins->region_masks && bins->region_count && bins->region_stride > 0, "null region-list buffer");
     const int W = view->width, H = view->height;
     const int gx = (W + RDG_TILE - 1) / RDG_TILE, gy = (H + RDG_TILE - 1) / RDG_TILE;
-    blend_bwd_kernel<<<gx * gy, 32 * BLEND_WARPS, 0, (cudaStream_t)stream>>>(
+    blend_bwd_kernel<<<(REGIONS * gx * gy + BLEND_WARPS - 1) / BLEND_WARPS, 32 * BLEND_WARPS, 0, (cudaStream_t)stream>>>(
         (const uint2*)bins->ranges, bins->region_ids, bins->region_masks, bins->region_stride, bins->region_count,
-        (const float4*)geom->p0, (const float4*)geom->p1, (const float2*)geom->p2, view->bg, W, H, gx, fwd->final_T,
+        (const float4*)geom->p0, (const float4*)geom->p1, (const float2*)geom->p2, view->bg, W, H, gx, gx * gy, fwd->final_T,
         fwd->n_contrib, dL_dcolor, dL_ddepth, dL_dalpha, acc);
     RDG_CHECK_LAUNCH();
     rdg_count_launches(1);

@@ -37,3 +37,12 @@ def rel_err(a, b):
     """max|a-b| / max|b| (norm-wise relative error used for gradients)."""
     denom = b.abs().max().item()
     return (a - b).abs().max().item() / max(denom, 1e-30)
+
+
+def elementwise_ok(got, ref, rtol=1e-3, floor=1e-5):
+    """Element-wise gradient bar |a - b| <= rtol |b| + floor max|b| (a tensor whose small entries are all wrong fails here,
+    while it would pass the norm-wise rel_err); returns (ok, worst |a - b| / bound)."""
+    got, ref = got.double().cpu(), ref.double().cpu()
+    bound = (rtol * ref.abs() + floor * ref.abs().max()).clamp_min(1e-300)
+    ratio = ((got - ref).abs() / bound).max().item()
+    return ratio <= 1.0, ratio

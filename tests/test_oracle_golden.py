@@ -87,3 +87,24 @@ def test_camera_conventions():
     assert abs(torch.linalg.det(R).item() - 1.0) < 1e-5
     p = cam.world_view_transform @ torch.tensor([0.0, 0.0, 4.0, 1.0])
     assert p[2] > 0 and abs(p[0]) < 1e-5 and abs(p[1]) < 1e-5
+
+
+def test_rasterizer_oracle_is_frozen():
+    """oracle/splat_oracle.py reproduces tests/golden/raster_small.npz (its own outputs, frozen by
+    tests/golden/make_golden_raster.py): integer outputs bit for bit, floats to summation-order noise.  The
+    rasterizer's reference source is absent, so this pins the oracle against drift, not against upstream."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import make_golden_raster as mg
+    frozen = np.load(os.path.join(GOLDEN, "raster_small.npz"))
+    data, meta = mg.build()
+    assert [meta["n"], meta["H"], meta["W"], meta["deg"]] == frozen["meta"].tolist()
+    for k in ("means3D", "opacities", "scales", "rotations", "shs", "viewmatrix", "projmatrix", "dL_dcolor"):
+        assert np.array_equal(data[k], frozen[k]), f"input {k} changed: the scene generator moved"
+    for k in ("radii", "tiles_touched", "keys", "vals", "ranges"):
+        assert np.array_equal(data[k], frozen[k]), k
+    for k in ("color", "depth", "alpha", "final_T"):
+        assert np.abs(data[k] - frozen[k]).max() <= 2e-6, k
+    for k in ("g_means3D", "g_means2D", "g_shs", "g_opacities", "g_scales", "g_rotations", "g_viewmatrix"):
+        ref = frozen[k]
+        assert np.abs(data[k] - ref).max() <= 1e-5 * np.abs(ref).max(), k
