@@ -169,6 +169,8 @@ uint64_t rdg_launch_count(void);
  *   "dtable_v1"    1: first version of the dL/dtable reduction
  *   "diff_smem"    1 (default): the preprocess kernels keep B(t) - table rows in shared memory when num_times <= 140;
  *                  0: every dynamic Gaussian gathers its 448-byte table row from global memory
+ *   "deterministic" 1: rdg_preprocess_bwd runs its kernels with one CTA so that the cross-CTA float atomics of dL/dV,
+ *                  dL/dtable and dL/dB(t) land in a fixed order (test mode, slow; pair it with rdg_blend_bwd_deterministic)
  * Returns RDG_E_ARG for an unknown name. */
 int rdg_set_tunable(const char* name, int32_t value);
 
@@ -207,6 +209,18 @@ int rdg_blend_fwd(int64_t n, const RdgGeom* geom, const RdgBins* bins, const Rdg
 int rdg_blend_bwd(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view,
                   const RdgImage* fwd, const float* dL_dcolor, const float* dL_ddepth,
                   const float* dL_dalpha, float* acc, void* stream);
+
+/* Run-to-run reproducible variant of rdg_blend_bwd (test mode: two passes over the lists).  rdg_blend_bwd sums the
+ * per-(Gaussian, region) partial gradients with float atomics, whose order - hence the last bits of acc - changes from run
+ * to run.  Here the partials are summed as 64-bit integers: pass 1 takes the largest magnitude of every accumulator
+ * (atomicMax), pass 2 adds round(partial * 2^(40 - exponent of that maximum)) with integer atomics, which are exact and
+ * order-independent, and a last kernel converts back to float (resolution 2^-40 of the largest partial; up to 2^22
+ * partials per accumulator).  acc is overwritten.  scratch: rdg_blend_bwd_deterministic_scratch_bytes(n) bytes, 8-byte
+ * aligned, contents irrelevant. */
+int64_t rdg_blend_bwd_deterministic_scratch_bytes(int64_t n);
+int rdg_blend_bwd_deterministic(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view,
+                                const RdgImage* fwd, const float* dL_dcolor, const float* dL_ddepth,
+                                const float* dL_dalpha, float* acc, void* scratch, int64_t scratch_bytes, void* stream);
 
 /* acc -> parameter gradients (+ pose, + deformation) (§8 a10, App. A.7). */
 int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, const RdgGeom* geom,
@@ -247,10 +261,19 @@ typedef struct RdgLossTerms {
     const float* alpha;      /* [1,H,W] rendered alpha */
     float w_alpha;
     float* dL_dalpha;        /* [1,H,W] overwritten with -w_alpha / (H W); may be NULL */
+    /* LocalPearsonDepthLoss (losses.py:132-182): mean over n_local_boxes boxes of 1 - Pearson(depth, gt_depth) inside the box,
+     * weight w_local (0.15 in every reference config); its gradient is ADDED to the global term in dL_ddepth within the same
+     * passes.  Boxes: device int32 [n,4] = (row0, col0, rows, cols); the reference draws row0 / col0 with torch.randint on the
+     * device every iteration (:149-150).  NULL / 0 = off.  Uses depth / gt_depth / pearson_eps / dL_ddepth from above
+     * (w_pearson may be 0). */
+    const int32_t* local_boxes;
+    int32_t n_local_boxes;   /* <= 256 */
+    float w_local;
 } RdgLossTerms;
 
 /* The whole per-iteration loss stage in three launches: rdg_l1_dssim plus the optional terms above.
- * out_loss (device, 8 floats) = {photometric loss, l1, ssim, 1 - Pearson, w_alpha * mean(1 - alpha), -, -, -};
+ * out_loss (device, 8 floats) = {photometric loss, l1, ssim, 1 - Pearson (global), w_alpha * mean(1 - alpha),
+ *                                mean_b (1 - Pearson_b) (local boxes), -, -};
  * entries of disabled terms are left untouched.  Workspace as for rdg_l1_dssim. */
 int rdg_losses(const float* pred, const float* gt, int32_t channels, int32_t height, int32_t width,
                float w_l1, float w_dssim, const RdgLossTerms* extra, float* out_loss, float* dL_dpred,

@@ -72,7 +72,8 @@ class RdgAdamGroup(C.Structure):
 
 class RdgLossTerms(C.Structure):
     _fields_ = [("depth", c_ptr), ("gt_depth", c_ptr), ("w_pearson", C.c_float), ("pearson_eps", C.c_float),
-                ("dL_ddepth", c_ptr), ("alpha", c_ptr), ("w_alpha", C.c_float), ("dL_dalpha", c_ptr)]
+                ("dL_ddepth", c_ptr), ("alpha", c_ptr), ("w_alpha", C.c_float), ("dL_dalpha", c_ptr),
+                ("local_boxes", c_ptr), ("n_local_boxes", C.c_int32), ("w_local", C.c_float)]
 
 
 class RdgBasisMlp(C.Structure):
@@ -107,6 +108,9 @@ SYMBOLS = {
                                 C.POINTER(RdgImage), c_ptr]),
     "rdg_blend_bwd": (C.c_int, [C.c_int64, C.POINTER(RdgGeom), C.POINTER(RdgBins), C.POINTER(RdgView),
                                 C.POINTER(RdgImage), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "rdg_blend_bwd_deterministic_scratch_bytes": (C.c_int64, [C.c_int64]),
+    "rdg_blend_bwd_deterministic": (C.c_int, [C.c_int64, C.POINTER(RdgGeom), C.POINTER(RdgBins), C.POINTER(RdgView),
+                                              C.POINTER(RdgImage), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr]),
     "rdg_preprocess_bwd": (C.c_int, [C.POINTER(RdgScene), C.POINTER(RdgView), C.POINTER(RdgGeom), c_ptr,
                                      C.POINTER(RdgSceneGrad), c_ptr]),
     "rdg_dcolor_from_acc": (C.c_int, [C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr]),

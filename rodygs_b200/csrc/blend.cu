@@ -588,12 +588,15 @@ __device__ __forceinline__ void rdg_bwd_quad(BwdPair& pa, BwdPair& pb, float Adx
     wb = rdg_mul2(rdg_pk(oG[2], oG[3]), dLb);
 }
 
+// DET: 0 = float atomics (the product path); 1 / 2 = the two passes of rdg_blend_bwd_deterministic: largest magnitude per
+// accumulator, then exact integer accumulation scaled by it.
+template <int DET>
 __global__ void __launch_bounds__(32 * BLEND_WARPS, BWD_MINB) blend_bwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ rl_ids, const uint8_t* __restrict__ rl_masks, int64_t stride,
     const uint32_t* __restrict__ rcount, const float4* __restrict__ p0, const float4* __restrict__ p1,
     const float2* __restrict__ p2, const float* __restrict__ bg, int W, int H, int gx, int n_tiles, const float* __restrict__ final_T,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
-    const float* __restrict__ dL_dalpha, float* __restrict__ acc) {
+    const float* __restrict__ dL_dalpha, float* __restrict__ acc, uint32_t* __restrict__ det_max, long long* __restrict__ det_sum) {
     __shared__ StagedW sm_all[BLEND_WARPS];
     __shared__ __align__(16) float pool_all[BLEND_WARPS][(POOL + 1) * PREC];   // + the scratch record of the null entry
     const BlendGeo geo = rdg_geo(gx, W, H);
@@ -798,10 +801,29 @@ __global__ void __launch_bounds__(32 * BLEND_WARPS, BWD_MINB) blend_bwd_kernel(
                 const float4 o0 = make_float4(-(cA * sx + cB * sy), -(cC * sy + cB * sx), -0.5f * s4.x, -s1.x);
                 const float4 o1 = make_float4(-0.5f * s1.y, s2.x / gb4.y, s2.y, s4.y);
                 const float4 o2 = make_float4(s3.x, s3.y, 0.f, 0.f);
-                float4* dst = reinterpret_cast<float4*>(acc + (size_t)((half ? idc_hi : idc_lo) & ~RDG_PW_FLAG) * NACC);
-                atomicAdd(dst + 0, o0);
-                atomicAdd(dst + 1, o1);
-                atomicAdd(dst + 2, o2);
+                const size_t arow = (size_t)((half ? idc_hi : idc_lo) & ~RDG_PW_FLAG) * NACC;
+                if (DET == 0) {
+                    float4* dst = reinterpret_cast<float4*>(acc + arow);
+                    atomicAdd(dst + 0, o0);
+                    atomicAdd(dst + 1, o1);
+                    atomicAdd(dst + 2, o2);
+                } else {
+                    const float vals[10] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y};
+#pragma unroll
+                    for (int c = 0; c < 10; ++c) {
+                        if (DET == 1) {
+                            atomicMax(det_max + arow + c, __float_as_uint(fabsf(vals[c])));
+                        } else {
+                            const float mx = __uint_as_float(det_max[arow + c]);
+                            if (mx > 0.0f && mx < 3.0e38f) {
+                                int ex;
+                                frexpf(mx, &ex);                   // mx = m 2^ex, m in [0.5, 1)
+                                const long long q = __double2ll_rn((double)vals[c] * ldexp(1.0, 40 - ex));
+                                atomicAdd(reinterpret_cast<unsigned long long*>(det_sum + arow + c), (unsigned long long)q);
+                            }
+                        }
+                    }
+                }
             }
         }
         done_slots += cnt2;
@@ -851,11 +873,64 @@ extern "C" int rdg_blend_bwd(int64_t n, const RdgGeom* geom, const RdgBins* bins
     RDG_CHECK_ARG(bins->region_ids && bins->region_masks && bins->region_count && bins->region_stride > 0, "null region-list buffer");
     const int W = view->width, H = view->height;
     const int gx = (W + RDG_TILE - 1) / RDG_TILE, gy = (H + RDG_TILE - 1) / RDG_TILE;
-    blend_bwd_kernel<<<(REGIONS * gx * gy + BLEND_WARPS - 1) / BLEND_WARPS, 32 * BLEND_WARPS, 0, (cudaStream_t)stream>>>(
+    blend_bwd_kernel<0><<<(REGIONS * gx * gy + BLEND_WARPS - 1) / BLEND_WARPS, 32 * BLEND_WARPS, 0, (cudaStream_t)stream>>>(
         (const uint2*)bins->ranges, bins->region_ids, bins->region_masks, bins->region_stride, bins->region_count,
         (const float4*)geom->p0, (const float4*)geom->p1, (const float2*)geom->p2, view->bg, W, H, gx, gx * gy, fwd->final_T,
-        fwd->n_contrib, dL_dcolor, dL_ddepth, dL_dalpha, acc);
+        fwd->n_contrib, dL_dcolor, dL_ddepth, dL_dalpha, acc, nullptr, nullptr);
     RDG_CHECK_LAUNCH();
     rdg_count_launches(1);
+    return RDG_OK;
+}
+
+// ---- deterministic variant (test mode) ----
+__global__ void det_finalize_kernel(int64_t n_vals, const uint32_t* __restrict__ det_max, const long long* __restrict__ det_sum,
+                                    float* __restrict__ acc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_vals) return;
+    const float mx = __uint_as_float(det_max[i]);
+    float v = 0.0f;
+    if (mx > 0.0f && mx < 3.0e38f) {
+        int ex;
+        frexpf(mx, &ex);
+        v = (float)((double)det_sum[i] * ldexp(1.0, ex - 40));
+    }
+    acc[i] = v;
+}
+
+extern "C" int64_t rdg_blend_bwd_deterministic_scratch_bytes(int64_t n) {
+    if (n < 0) return RDG_E_ARG;
+    return rdg_align_up(n * NACC * (int64_t)sizeof(long long), 256) + rdg_align_up(n * NACC * (int64_t)sizeof(uint32_t), 256);
+}
+
+extern "C" int rdg_blend_bwd_deterministic(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view,
+                                           const RdgImage* fwd, const float* dL_dcolor, const float* dL_ddepth,
+                                           const float* dL_dalpha, float* acc, void* scratch, int64_t scratch_bytes, void* stream) {
+    RDG_CHECK_ARG(geom && bins && view && fwd && acc && scratch, "null argument");
+    RDG_CHECK_ARG(fwd->final_T && fwd->n_contrib, "null forward state");
+    RDG_CHECK_ARG(bins->region_ids && bins->region_masks && bins->region_count && bins->region_stride > 0, "null region-list buffer");
+    if (scratch_bytes < rdg_blend_bwd_deterministic_scratch_bytes(n)) {
+        rdg_set_error("rdg_blend_bwd_deterministic: scratch too small");
+        return RDG_E_CAPACITY;
+    }
+    if (n == 0) return RDG_OK;
+    const int W = view->width, H = view->height;
+    const int gx = (W + RDG_TILE - 1) / RDG_TILE, gy = (H + RDG_TILE - 1) / RDG_TILE;
+    cudaStream_t s = (cudaStream_t)stream;
+    long long* det_sum = (long long*)scratch;
+    uint32_t* det_max = (uint32_t*)((char*)scratch + rdg_align_up(n * NACC * (int64_t)sizeof(long long), 256));
+    RDG_CUDA(cudaMemsetAsync(scratch, 0, (size_t)rdg_blend_bwd_deterministic_scratch_bytes(n), s));
+    const int grid = (REGIONS * gx * gy + BLEND_WARPS - 1) / BLEND_WARPS;
+    blend_bwd_kernel<1><<<grid, 32 * BLEND_WARPS, 0, s>>>(
+        (const uint2*)bins->ranges, bins->region_ids, bins->region_masks, bins->region_stride, bins->region_count,
+        (const float4*)geom->p0, (const float4*)geom->p1, (const float2*)geom->p2, view->bg, W, H, gx, gx * gy, fwd->final_T,
+        fwd->n_contrib, dL_dcolor, dL_ddepth, dL_dalpha, acc, det_max, det_sum);
+    blend_bwd_kernel<2><<<grid, 32 * BLEND_WARPS, 0, s>>>(
+        (const uint2*)bins->ranges, bins->region_ids, bins->region_masks, bins->region_stride, bins->region_count,
+        (const float4*)geom->p0, (const float4*)geom->p1, (const float2*)geom->p2, view->bg, W, H, gx, gx * gy, fwd->final_T,
+        fwd->n_contrib, dL_dcolor, dL_ddepth, dL_dalpha, acc, det_max, det_sum);
+    const int64_t n_vals = n * NACC;
+    det_finalize_kernel<<<rdg_div_up(n_vals, 256), 256, 0, s>>>(n_vals, det_max, det_sum, acc);
+    RDG_CHECK_LAUNCH();
+    rdg_count_launches(3);
     return RDG_OK;
 }

@@ -9,7 +9,11 @@
 // applies the chain rule.  24 B/px read + 36 B/px maps written, then 36 + 24 B/px read +
 // 12 B/px written (the reference's conv2d chain moves ~700 B/px).  The global Pearson
 // depth statistics and the alpha regulariser ride on the channel-0 CTAs of pass 1, their
-// gradients on pass 2, so the whole loss stage is three launches.
+// gradients on pass 2, so the whole loss stage is three launches.  The LOCAL Pearson term (LocalPearsonDepthLoss,
+// /root/reference/src/trainer/losses.py:132-182: ~60 random 128x128 boxes at 1080p, a Python loop of ~25 kernels each in
+// the reference) rides along as well: a channel-0 CTA of pass 1 adds its pixels to the statistics of the boxes that
+// overlap its tile (0.7 boxes per tile on average), the finalize kernel turns them into per-box coefficients, and pass
+// 2 adds every covering box's term to the pixel's dL/ddepth - no atomics on the gradient, no extra pass over the image.
 #include <math.h>
 #include "common.cuh"
 
@@ -32,7 +36,16 @@ __constant__ float c_taps[11] = {1.028380124e-03f, 7.598758209e-03f, 3.600077331
 struct LossHdr {
     double sums[8];   // 0 ssim, 1 |x-y|, 2..6 depth: sum p, g, pp, gg, pg, 7 sum(1 - alpha)
     float coef[8];    // 0 mean g, 1 mean p, 2 d/d(g - mg), 3 d/d(p - mp)  (dL/ddepth = c2 (g-mg) + c3 (p-mp)), 4 dL/dalpha
+    double local_sum; // sum over the boxes of (1 - Pearson_b)
 };
+#define LOCAL_BOXES_MAX 256
+// local-box scratch behind the derivative maps: 8 doubles of statistics + 4 floats of coefficients per box
+struct __align__(16) LocalBox {
+    float coef[4];    // mean g, mean p, d/d(g - mg), d/d(p - mp), weight included (read as one float4)
+    double st[5];     // sum p, g, pp, gg, pg over the box
+    int pad[2];
+};
+static_assert(sizeof(LocalBox) == 64, "LocalBox layout");
 
 // Separable 11-tap blur of an SHL x SHL halo tile down to ST x ST, register-tiled: the horizontal pass
 // gives every thread one row and SEG adjacent outputs (each input is loaded once and used for up to 11
@@ -62,7 +75,8 @@ __global__ void __launch_bounds__(LTHREADS) ssim_fwd_kernel(const float* __restr
                                                             int H, int W, float* __restrict__ map_mu,
                                                             float* __restrict__ map_s1, float* __restrict__ map_s12,
                                                             LossHdr* __restrict__ hdr, const float* __restrict__ depth,
-                                                            const float* __restrict__ gt_depth, const float* __restrict__ alpha) {
+                                                            const float* __restrict__ gt_depth, const float* __restrict__ alpha,
+                                                            const int4* __restrict__ boxes, int n_boxes, LocalBox* __restrict__ lbox) {
     __shared__ float in[2][SHL][IPITCH];
     __shared__ float hz[5][SHL][HPITCH];
     __shared__ double red[8][LTHREADS / 32];
@@ -114,6 +128,9 @@ __global__ void __launch_bounds__(LTHREADS) ssim_fwd_kernel(const float* __restr
     const int x = blockIdx.x * ST + c;
     float ssim_v = 0.f, l1_v = 0.f;
     double st[6] = {0, 0, 0, 0, 0, 0};
+    float dp[VSEG], dg[VSEG];                                     // this thread's depth pixels (channel-0 CTAs)
+#pragma unroll
+    for (int i = 0; i < VSEG; ++i) dp[i] = dg[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < VSEG; ++i) {
         const int y = blockIdx.y * ST + vs * VSEG + i;
@@ -139,7 +156,8 @@ __global__ void __launch_bounds__(LTHREADS) ssim_fwd_kernel(const float* __restr
             l1_v += fabsf(in[0][r][c + HALO] - in[1][r][c + HALO]);
             if (ch == 0) {
                 if (depth) {
-                    const double p = depth[hwpix], g = gt_depth[hwpix];
+                    dp[i] = depth[hwpix]; dg[i] = gt_depth[hwpix];
+                    const double p = dp[i], g = dg[i];
                     st[0] += p; st[1] += g; st[2] += p * p; st[3] += g * g; st[4] += p * g;
                 }
                 if (alpha) st[5] += (double)(1.0f - alpha[hwpix]);
@@ -165,6 +183,30 @@ __global__ void __launch_bounds__(LTHREADS) ssim_fwd_kernel(const float* __restr
         for (int w = 0; w < LTHREADS / 32; ++w) t += red[threadIdx.x][w];
         atomicAdd(&hdr->sums[threadIdx.x], t);
     }
+    // local Pearson boxes that overlap this tile (uniform loop; a 128x128 box overlaps ~1 % of the 32x32 tiles)
+    if (ch == 0 && depth && n_boxes > 0) {
+        const int tx0 = blockIdx.x * ST, ty0 = blockIdx.y * ST;
+        for (int b = 0; b < n_boxes; ++b) {
+            const int4 bx = boxes[b];                             // row0, col0, rows, cols
+            if (bx.x >= ty0 + ST || bx.x + bx.z <= ty0 || bx.y >= tx0 + ST || bx.y + bx.w <= tx0) continue;
+            double s5[5] = {0, 0, 0, 0, 0};
+            const bool xin = x >= bx.y && x < bx.y + bx.w && x < W;
+#pragma unroll
+            for (int i = 0; i < VSEG; ++i) {
+                const int y = blockIdx.y * ST + vs * VSEG + i;
+                if (xin && y >= bx.x && y < bx.x + bx.z && y < H) {
+                    const double p = dp[i], g = dg[i];
+                    s5[0] += p; s5[1] += g; s5[2] += p * p; s5[3] += g * g; s5[4] += p * g;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) s5[k] += __shfl_xor_sync(0xffffffffu, s5[k], off);
+                if (lane == 0 && s5[k] != 0.0) atomicAdd(&lbox[b].st[k], s5[k]);
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(LTHREADS) ssim_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
@@ -173,7 +215,8 @@ __global__ void __launch_bounds__(LTHREADS) ssim_bwd_kernel(const float* __restr
                                                             float k_ssim, float k_l1, float* __restrict__ dL_dpred,
                                                             const LossHdr* __restrict__ hdr, const float* __restrict__ depth,
                                                             const float* __restrict__ gt_depth, float* __restrict__ dL_ddepth,
-                                                            float* __restrict__ dL_dalpha) {
+                                                            float* __restrict__ dL_dalpha, const int4* __restrict__ boxes, int n_boxes,
+                                                            const LocalBox* __restrict__ lbox) {
     __shared__ float in[3][SHL][IPITCH];
     __shared__ float hz[3][SHL][HPITCH];
     const int ch = blockIdx.z;
@@ -222,6 +265,29 @@ __global__ void __launch_bounds__(LTHREADS) ssim_bwd_kernel(const float* __restr
     blur_vertical<3>(hz, c, vs, o);
     const int x = blockIdx.x * ST + c;
     const bool do_depth = ch == 0 && dL_ddepth != nullptr, do_alpha = ch == 0 && dL_dalpha != nullptr;
+    // the local boxes that overlap this tile, in box order (warp 0, ballot compaction: the per-pixel sum keeps one order)
+    __shared__ int near_box[LOCAL_BOXES_MAX];
+    __shared__ int n_near_s;
+    if (do_depth && n_boxes > 0) {
+        if (threadIdx.x < 32) {
+            const int tx0 = blockIdx.x * ST, ty0 = blockIdx.y * ST;
+            int cnt = 0;
+            for (int base = 0; base < n_boxes; base += 32) {
+                const int b = base + (int)threadIdx.x;
+                bool hit = false;
+                if (b < n_boxes) {
+                    const int4 bx = boxes[b];
+                    hit = !(bx.x >= ty0 + ST || bx.x + bx.z <= ty0 || bx.y >= tx0 + ST || bx.y + bx.w <= tx0);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                if (hit) near_box[cnt + __popc(bal & ((1u << threadIdx.x) - 1u))] = b;
+                cnt += __popc(bal);
+            }
+            if (threadIdx.x == 0) n_near_s = cnt;
+        }
+        __syncthreads();
+    }
+    const int n_near = (do_depth && n_boxes > 0) ? n_near_s : 0;
     float mg = 0.f, mp = 0.f, cg = 0.f, cp = 0.f, ca = 0.f;
     if (do_depth) { mg = hdr->coef[0]; mp = hdr->coef[1]; cg = hdr->coef[2]; cp = hdr->coef[3]; }
     if (do_alpha) ca = hdr->coef[4];
@@ -235,7 +301,19 @@ __global__ void __launch_bounds__(LTHREADS) ssim_bwd_kernel(const float* __restr
             const float diff = xv - yv;
             const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
             dL_dpred[pix] = k_ssim * dssim + k_l1 * sgn;
-            if (do_depth) dL_ddepth[hwpix] = cg * (gt_depth[hwpix] - mg) + cp * (depth[hwpix] - mp);
+            if (do_depth) {
+                const float g = gt_depth[hwpix], pv = depth[hwpix];
+                float acc = cg * (g - mg) + cp * (pv - mp);
+                for (int k = 0; k < n_near; ++k) {                // every local box that covers this pixel adds its term
+                    const int b = near_box[k];
+                    const int4 bx = boxes[b];
+                    if (y >= bx.x && y < bx.x + bx.z && x >= bx.y && x < bx.y + bx.w) {
+                        const float4 c4 = *reinterpret_cast<const float4*>(lbox[b].coef);
+                        acc += c4.z * (g - c4.x) + c4.w * (pv - c4.y);
+                    }
+                }
+                dL_ddepth[hwpix] = acc;
+            }
             if (do_alpha) dL_dalpha[hwpix] = ca;
         }
     }
@@ -272,9 +350,42 @@ __global__ void loss_finalize_kernel(LossHdr* __restrict__ hdr, double n, double
     }
 }
 
+// LocalPearsonDepthLoss (losses.py:132-182): loss = mean_b (1 - Pearson_b); one thread per box
+__global__ void local_pearson_finalize_kernel(LossHdr* __restrict__ hdr, const int4* __restrict__ boxes, int n_boxes,
+                                              LocalBox* __restrict__ lbox, float w_local, float eps, float* __restrict__ out) {
+    __shared__ double part[LOCAL_BOXES_MAX];
+    const int b = threadIdx.x;
+    double loss_b = 0.0;
+    if (b < n_boxes) {
+        const int4 bx = boxes[b];
+        const double m = (double)bx.z * (double)bx.w;
+        const double* st = lbox[b].st;
+        const double mp = st[0] / m, mg = st[1] / m;
+        const double varp = fmax((st[2] - m * mp * mp) / (m - 1.0), 0.0), varg = fmax((st[3] - m * mg * mg) / (m - 1.0), 0.0);
+        const double sp = sqrt(varp), sg = sqrt(varg);
+        const double a = sp + (double)eps, bb = sg + (double)eps;
+        const double spg = st[4] - m * mp * mg;
+        loss_b = 1.0 - spg / (m * a * bb);
+        const double wgt = (double)w_local / (double)n_boxes;
+        const double k1 = 1.0 / (m * a * bb);
+        const double k2 = sp > 0.0 ? spg / (m * a * a * bb) / ((m - 1.0) * sp) : 0.0;
+        lbox[b].coef[0] = (float)mg;
+        lbox[b].coef[1] = (float)mp;
+        lbox[b].coef[2] = (float)(-wgt * k1);
+        lbox[b].coef[3] = (float)(wgt * k2);
+    }
+    part[threadIdx.x] = loss_b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < n_boxes; ++k) t += part[k];           // fixed order: reproducible
+        out[5] = (float)(t / (double)n_boxes);
+    }
+}
+
 extern "C" int64_t rdg_l1_dssim_workspace_bytes(int32_t channels, int32_t height, int32_t width) {
     if (channels <= 0 || height <= 0 || width <= 0) return RDG_E_ARG;
-    return 256 + (int64_t)3 * channels * height * width * (int64_t)sizeof(float);
+    return 256 + (int64_t)3 * channels * height * width * (int64_t)sizeof(float) + (int64_t)LOCAL_BOXES_MAX * (int64_t)sizeof(LocalBox);
 }
 
 extern "C" int rdg_losses(const float* pred, const float* gt, int32_t channels, int32_t height, int32_t width,
@@ -288,30 +399,42 @@ extern "C" int rdg_losses(const float* pred, const float* gt, int32_t channels, 
     }
     const bool use_depth = extra && extra->depth && extra->gt_depth && extra->w_pearson != 0.0f;
     const bool use_alpha = extra && extra->alpha && extra->w_alpha != 0.0f;
+    const bool use_local = extra && extra->depth && extra->gt_depth && extra->local_boxes && extra->n_local_boxes > 0 &&
+                           extra->w_local != 0.0f;
+    RDG_CHECK_ARG(!use_local || extra->n_local_boxes <= LOCAL_BOXES_MAX, "at most 256 local Pearson boxes");
+    RDG_CHECK_ARG(!(use_local && dL_dpred) || extra->dL_ddepth, "the local Pearson term needs dL_ddepth");
+    const bool any_depth = use_depth || use_local;
     cudaStream_t s = (cudaStream_t)stream;
     LossHdr* hdr = (LossHdr*)workspace;
     const size_t plane = (size_t)channels * height * width;
     float* maps = (float*)((char*)workspace + 256);
+    LocalBox* lbox = (LocalBox*)((char*)workspace + 256 + 3 * plane * sizeof(float));
+    const int4* boxes = use_local ? (const int4*)extra->local_boxes : nullptr;
+    const int n_boxes = use_local ? extra->n_local_boxes : 0;
     RDG_CUDA(cudaMemsetAsync(hdr, 0, sizeof(LossHdr), s));
+    if (use_local) RDG_CUDA(cudaMemsetAsync(lbox, 0, (size_t)n_boxes * sizeof(LocalBox), s));
     const dim3 grid((width + ST - 1) / ST, (height + ST - 1) / ST, channels);
     const bool need_grad = dL_dpred != nullptr;
     ssim_fwd_kernel<<<grid, LTHREADS, 0, s>>>(pred, gt, height, width, need_grad ? maps : nullptr,
                                              need_grad ? maps + plane : nullptr, need_grad ? maps + 2 * plane : nullptr, hdr,
-                                             use_depth ? extra->depth : nullptr, use_depth ? extra->gt_depth : nullptr,
-                                             use_alpha ? extra->alpha : nullptr);
+                                             any_depth ? extra->depth : nullptr, any_depth ? extra->gt_depth : nullptr,
+                                             use_alpha ? extra->alpha : nullptr, boxes, n_boxes, lbox);
     RDG_CHECK_LAUNCH();
     const double n = (double)plane, npix = (double)height * (double)width;
     loss_finalize_kernel<<<1, 1, 0, s>>>(hdr, n, npix, w_l1, w_dssim, use_depth ? 1 : 0, use_depth ? extra->w_pearson : 0.f,
                                          use_depth ? extra->pearson_eps : 0.f, use_alpha ? 1 : 0,
                                          use_alpha ? extra->w_alpha : 0.f, out_loss);
+    if (use_local)
+        local_pearson_finalize_kernel<<<1, LOCAL_BOXES_MAX, 0, s>>>(hdr, boxes, n_boxes, lbox, extra->w_local, extra->pearson_eps, out_loss);
     if (need_grad) {
         ssim_bwd_kernel<<<grid, LTHREADS, 0, s>>>(pred, gt, height, width, maps, maps + plane, maps + 2 * plane,
                                                  (float)(-(double)w_dssim / n), (float)((double)w_l1 / n), dL_dpred, hdr,
-                                                 use_depth ? extra->depth : nullptr, use_depth ? extra->gt_depth : nullptr,
-                                                 use_depth ? extra->dL_ddepth : nullptr, use_alpha ? extra->dL_dalpha : nullptr);
+                                                 any_depth ? extra->depth : nullptr, any_depth ? extra->gt_depth : nullptr,
+                                                 any_depth ? extra->dL_ddepth : nullptr, use_alpha ? extra->dL_dalpha : nullptr,
+                                                 boxes, n_boxes, lbox);
     }
     RDG_CHECK_LAUNCH();
-    rdg_count_launches(need_grad ? 3 : 2);
+    rdg_count_launches((need_grad ? 3 : 2) + (use_local ? 1 : 0));
     return RDG_OK;
 }
 

@@ -587,6 +587,8 @@ template <bool RAW, int DEG>
 static int launch_bwd(const PreBwdParams& p, int grid, size_t smem, cudaStream_t s) {
     const int cap = rdg_tunable(RDG_TUN_PRE_GRID_CAP);
     if (cap > 0 && grid > cap) grid = cap;
+    // deterministic mode: ONE persistent CTA walks every chunk, so the per-CTA atomics of dL/dV land in a fixed order
+    if (rdg_tunable(RDG_TUN_DETERMINISTIC) != 0) grid = 1;
     RDG_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<RAW, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     preprocess_bwd_kernel<RAW, DEG><<<grid, RDG_BLOCK, smem, s>>>(p);
     RDG_CHECK_LAUNCH();
@@ -644,7 +646,8 @@ extern "C" int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, co
             int slices = (3200 + scene->num_times - 1) / scene->num_times;
             slices = slices < 1 ? 1 : (slices > 32 ? 32 : slices);
             const int64_t items = (int64_t)scene->num_times * slices;
-            const int g = (int)(items < RDG_SM_COUNT * 4 ? items : RDG_SM_COUNT * 4);
+            int g = (int)(items < RDG_SM_COUNT * 4 ? items : RDG_SM_COUNT * 4);
+            if (rdg_tunable(RDG_TUN_DETERMINISTIC) != 0) g = 1;   // one CTA: the slices of a frame add to dL/dtable in a fixed order
             dtable2_kernel<<<g, 128, 0, s>>>(scene->frame_order, scene->frame_offsets, scene->motion_coeff,
                                              grads->g7_scratch, scene->num_basis, scene->num_times, slices, grads->table,
                                              grads->basis_t);

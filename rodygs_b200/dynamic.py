@@ -67,14 +67,14 @@ class _FusedDynamicRender(torch.autograd.Function):
         coeff = None
         if deform:
             coeff = _f32c(motion_coeff).reshape(nd, -1)
-            if time_ind.dtype != torch.int32:
-                time_ind = time_ind.to(torch.int32)
             basis_t, table = _f32c(basis_t), _f32c(table)
             if coeff.shape[1] > 16 or basis_t.shape != (coeff.shape[1], 7) or table.shape[1:] != (coeff.shape[1], 7):
                 raise Exception("motion_coeff [Nd,(1,)K<=16], basis_t [K,7] and table [T,K,7] are required")
-        order, offsets = engine.frame_csr(time_ind, table.shape[0]) if deform else (None, None)
+        order = offsets = None
+        if deform:
+            time_ind, order, offsets = engine.frame_csr_of(time_ind, table.shape[0])
         scene = SceneArgs(st=st, dy=dy, raw=True, use_deform=deform, motion_coeff=coeff, frame_order=order, frame_offsets=offsets,
-                          time_ind=time_ind.contiguous() if deform else None, basis_t=basis_t if deform else None,
+                          time_ind=time_ind if deform else None, basis_t=basis_t if deform else None,
                           table=table if deform else None, spatial_lr_scale=float(spatial_lr_scale))
         view = ViewArgs(height=settings.image_height, width=settings.image_width, tanfovx=settings.tanfovx,
                         tanfovy=settings.tanfovy, scale_modifier=settings.scale_modifier, sh_degree=settings.sh_degree,

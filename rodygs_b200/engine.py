@@ -45,6 +45,10 @@ class Config:
     #          emission-order arrays (point_offsets, unsorted keys/values) that the tests pin.
     binning: str = "tiles"
     emit_sorted_keys: bool = True       # write the sorted 64-bit keys (only verification reads them)
+    # Run-to-run reproducible backward pass (test mode, several times slower): the blend backward sums its per-region
+    # partials as scaled 64-bit integers (rdg_blend_bwd_deterministic) and the per-Gaussian backward runs on one CTA so that
+    # the cross-CTA atomics of dL/dV, dL/dtable, dL/dB(t) keep one order.  Also switched on by RDG_DETERMINISTIC=1.
+    deterministic: bool = os.environ.get("RDG_DETERMINISTIC", "0") == "1"
 
 
 config = Config()
@@ -219,18 +223,35 @@ _csr_cache: Dict[tuple, tuple] = {}
 
 def frame_csr(time_ind: torch.Tensor, num_times: int):
     """CSR of the dynamic Gaussians by birth frame: (order [nd] int32, offsets [T+1] int32).
-    Built on the device once per `time_ind` tensor (it only changes on densification) and cached."""
-    key = (time_ind.data_ptr(), time_ind._version, time_ind.numel(), int(num_times), time_ind.device.index)
+    Built on the device once per `time_ind` tensor (it only changes on densification) and cached.  The cache entry keeps
+    the tensor itself alive and is only reused for that very object at the same version: a recycled address (temporaries
+    of the caching allocator) or an in-place rewrite through a raw pointer cannot alias a stale entry - callers that
+    write time_ind through the C ABI (densification) build a new tensor, SplatTrainStep keeps its own CSR."""
+    key = (id(time_ind), int(num_times))
     hit = _csr_cache.get(key)
-    if hit is not None:
-        return hit
+    if hit is not None and hit[0] is time_ind and hit[1] == time_ind._version:
+        return hit[2]
     if len(_csr_cache) > 16:
         _csr_cache.clear()
     ti = time_ind.long()
     sorted_ti, order = torch.sort(ti, stable=True)
     offsets = torch.searchsorted(sorted_ti, torch.arange(num_times + 1, device=ti.device))
     out = (order.to(torch.int32).contiguous(), offsets.to(torch.int32).contiguous())
-    _csr_cache[key] = out
+    _csr_cache[key] = (time_ind, time_ind._version, out)
+    return out
+
+
+def frame_csr_of(time_ind: torch.Tensor, num_times: int):
+    """(time_ind as contiguous int32, order, offsets) for a `gaussian_to_time_ind` of any integer dtype (the reference keeps
+    it as int64, rodygs_dynamic.py:58-77), cached on the caller's tensor object like frame_csr."""
+    key = (id(time_ind), int(num_times), "any")
+    hit = _csr_cache.get(key)
+    if hit is not None and hit[0] is time_ind and hit[1] == time_ind._version:
+        return hit[2]
+    ti32 = time_ind if (time_ind.dtype == torch.int32 and time_ind.is_contiguous()) else time_ind.to(torch.int32).contiguous()
+    order, offsets = frame_csr(ti32, num_times)
+    out = (ti32, order, offsets)
+    _csr_cache[key] = (time_ind, time_ind._version, out)
     return out
 
 
@@ -383,8 +404,15 @@ def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: Sce
         return None if t is None else t.contiguous()
 
     dL_dcolor, dL_ddepth, dL_dalpha = c(dL_dcolor), c(dL_ddepth), c(dL_dalpha)
-    check(lib.rdg_blend_bwd(n, C.byref(gm_s), C.byref(bins), C.byref(vw_s), C.byref(img),
-                            ptr(dL_dcolor), ptr(dL_ddepth), ptr(dL_dalpha), ptr(acc), stream))
+    _lib.set_tunable("deterministic", 1 if config.deterministic else 0)
+    if config.deterministic:
+        nb = int(lib.rdg_blend_bwd_deterministic_scratch_bytes(n))
+        scratch = torch.empty(max(nb, 8), dtype=torch.uint8, device=dev)
+        check(lib.rdg_blend_bwd_deterministic(n, C.byref(gm_s), C.byref(bins), C.byref(vw_s), C.byref(img), ptr(dL_dcolor),
+                                              ptr(dL_ddepth), ptr(dL_dalpha), ptr(acc), ptr(scratch), nb, stream))
+    else:
+        check(lib.rdg_blend_bwd(n, C.byref(gm_s), C.byref(bins), C.byref(vw_s), C.byref(img),
+                                ptr(dL_dcolor), ptr(dL_ddepth), ptr(dL_dalpha), ptr(acc), stream))
     early = after_blend is not None and grads.dcolor is not None and state.scene.colors_precomp is None
     if early:
         check(lib.rdg_dcolor_from_acc(n, ptr(acc), ptr(state.geom["clamped"]), ptr(grads.dcolor), stream))

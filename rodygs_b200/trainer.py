@@ -97,23 +97,38 @@ class SplatTrainStep:
 
     loss = w_l1 * L1 + w_dssim * (1 - SSIM)                 (train_kubric_mrig.yaml:135-144)
          + w_pearson * (1 - Pearson(depth, gt_depth))       (:145-150, global)
+         + w_local * mean_b (1 - Pearson_b)                 (:151-158, LocalPearsonDepthLoss over random box_p x box_p boxes,
+                                                             losses.py:132-182; n = int(p_corr * (H // box_p) * (W // box_p)))
          + w_alpha * mean(1 - alpha)                        (benchmark-only term)
+    All of it is ONE loss stage (rdg_losses: three passes + a one-block finalize for the boxes).
     """
 
     def __init__(self, scene: Dict, height: int, width: int, sh_degree: int = 3, w_l1: float = 0.8,
                  w_dssim: float = 0.2, w_pearson: float = 0.05, w_alpha: float = 0.0, device="cuda",
-                 process_group=None):
+                 process_group=None, w_local: float = 0.15, box_p: int = 128, p_corr: float = 0.5):
         self.dev = torch.device(device)
         self.H, self.W, self.sh_degree = int(height), int(width), int(sh_degree)
         self.w = (float(w_l1), float(w_dssim), float(w_pearson), float(w_alpha))
+        # LocalPearsonDepthLoss(box_p=128, p_corr=0.5), weight 0.15 in every reference config
+        self.w_local, self.box_p = float(w_local), int(box_p)
+        self.n_local = int(p_corr * math.floor(self.H / self.box_p) * math.floor(self.W / self.box_p)) if w_local != 0.0 else 0
         self.pg = process_group
         self.optim: Dict[str, "GaussianAdam"] = {}
+        self._skip_step = set()             # models whose next optimizer_step is the reference's post-densification no-op
         self.stats: Dict[str, "DensifyStats"] = {}
         self._load_scene(scene)
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.bg = torch.zeros(3, dtype=torch.float32, device=self.dev)          # rodygs.py:267
         self.view_grad = torch.zeros(4, 4, **f32)
-        self.loss_parts = torch.zeros(8, **f32)   # [0:3] photometric (loss, l1, ssim), [3] pearson, [4] alpha term
+        self.loss_parts = torch.zeros(8, **f32)   # [0:3] photometric (loss, l1, ssim), [3] pearson, [4] alpha term, [5] local pearson
+        if self.n_local > 0:
+            # boxes (row0, col0, rows, cols): the origins are redrawn on the device every step like the reference does
+            # (torch.randint(0, max_h) / (0, max_w), losses.py:149-150): one randint launch + one remainder launch
+            self._boxes = torch.zeros(self.n_local, 4, dtype=torch.int32, device=self.dev)
+            self._boxes[:, 2:] = self.box_p
+            self._box_limits = torch.tensor([self.H - self.box_p, self.W - self.box_p], dtype=torch.int32, device=self.dev)
+            self._box_rand = torch.empty(self.n_local, 2, dtype=torch.int32, device=self.dev)
+        self.local_box_origins = None             # tests: fixed [n, 2] (row0, col0) instead of the random draw
         self.dL_dcolor = torch.empty(3, self.H, self.W, **f32)
         self.dL_ddepth = torch.zeros(1, self.H, self.W, **f32)
         self.dL_dalpha = torch.zeros(1, self.H, self.W, **f32)
@@ -205,6 +220,12 @@ class SplatTrainStep:
             ev.record()
             self.stage_events.append((name, ev))
 
+    def _check_input(self, name: str, t: torch.Tensor, shape):
+        if not torch.is_tensor(t) or t.dtype != torch.float32 or t.device != self.params.device or not t.is_contiguous() \
+                or tuple(t.shape) != tuple(shape):
+            got = f"{tuple(t.shape)} {t.dtype} {t.device} contiguous={t.is_contiguous()}" if torch.is_tensor(t) else type(t).__name__
+            raise ValueError(f"SplatTrainStep: {name} must be a contiguous float32 tensor of shape {tuple(shape)} on {self.params.device}, got {got}")
+
     # -- one view --------------------------------------------------------------------------------
     def forward_backward(self, viewmatrix: torch.Tensor, projmatrix: torch.Tensor, tanfovx: float, tanfovy: float,
                          basis_t: torch.Tensor, gt_image: torch.Tensor, gt_depth: Optional[torch.Tensor],
@@ -217,6 +238,15 @@ class SplatTrainStep:
         lib = _lib.load()
         stream = _lib.stream_ptr()
         deform = self.nd > 0
+        # the kernels take raw pointers: refuse anything that is not the fp32 contiguous CUDA tensor of the expected shape
+        self._check_input("viewmatrix", viewmatrix, (4, 4))
+        self._check_input("projmatrix", projmatrix, (4, 4))
+        if deform:
+            self._check_input("basis_t", basis_t, (self.num_basis, 7))
+        if not forward_only:
+            self._check_input("gt_image", gt_image, (3, self.H, self.W))
+            if gt_depth is not None:
+                self._check_input("gt_depth", gt_depth, (1, self.H, self.W))
         scene = SceneArgs(st=self._set("static"), dy=self._set("dynamic"), raw=True, use_deform=deform,
                           motion_coeff=self.p("motion_coeff").view(self.nd, self.num_basis) if deform else None,
                           time_ind=self.time_ind if deform else None, basis_t=basis_t if deform else None,
@@ -232,12 +262,20 @@ class SplatTrainStep:
             return None
         # ---- losses + their gradients w.r.t. the rendered maps (fused kernels) ----
         w_l1, w_ds, w_p, w_a = self.w
-        use_depth = w_p != 0.0 and gt_depth is not None
+        use_local = self.n_local > 0 and gt_depth is not None
+        use_depth = (w_p != 0.0 or use_local) and gt_depth is not None
         use_alpha = w_a != 0.0
         terms = _lib.RdgLossTerms()
         if use_depth:
             terms.depth, terms.gt_depth, terms.dL_ddepth = ptr(depth), ptr(gt_depth), ptr(self.dL_ddepth)
             terms.w_pearson, terms.pearson_eps = w_p, 1e-6
+        if use_local:
+            if self.local_box_origins is not None:
+                self._boxes[:, :2].copy_(self.local_box_origins.to(self.dev, torch.int32))
+            else:
+                self._box_rand.random_(0, 1 << 30)
+                torch.remainder(self._box_rand, self._box_limits, out=self._boxes[:, :2])
+            terms.local_boxes, terms.n_local_boxes, terms.w_local = ptr(self._boxes), self.n_local, self.w_local
         if use_alpha:
             terms.alpha, terms.dL_dalpha, terms.w_alpha = ptr(alpha), ptr(self.dL_dalpha), w_a
         # loss_parts[0:5] are written by the finalize kernel; disabled terms keep their zero
@@ -297,6 +335,8 @@ class SplatTrainStep:
         n = self.ns + self.nd
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.views_per_rank, self.world_size = int(views_per_rank), int(world_size)
+        if self.views_per_rank * self.world_size > 16:
+            raise ValueError("factored exchange: rdg_sh_grad_views stages at most 16 views per step (views_per_rank * world_size)")
         self._fx_args = (views_per_rank, world_size, copy_engine_gather, gather_streams)
         v_total = self.views_per_rank * self.world_size
         self._symm = None
@@ -364,6 +404,9 @@ class SplatTrainStep:
         r*views_per_rank ..); the result in self.grads is the mean over the V views."""
         lib = _lib.load()
         v_total = self.views_per_rank * self.world_size
+        self._check_input("viewmats_all", viewmats_all, (v_total, 4, 4))
+        if self.nd > 0:
+            self._check_input("basis_all", basis_all, (v_total, self.num_basis, 7))
         n_plain = sh_start(self.layout)
         cur = torch.cuda.current_stream()
         if not self._gather_started:
@@ -391,7 +434,7 @@ class SplatTrainStep:
         self._mark("exchange")
 
     # -- motion-basis MLP ----------------------------------------------------------------
-    def attach_basis_mlp(self, mlp, train_times: torch.Tensor, lr: float = 0.0):
+    def attach_basis_mlp(self, mlp, train_times: torch.Tensor, lr: float = 1.6e-3):
         """mlp: rodygs_b200.deform.BasisMLP.  train_times [T]: the dataset's normalised frame times, whose
         embeddings the reference caches as `_time_batch_embeddings` (rodygs_dynamic.py:58-77).  After this,
         basis_forward(t) fills B(t) and the table of the flat PARAMETER buffer straight from the network and
@@ -399,8 +442,9 @@ class SplatTrainStep:
         assert train_times.numel() == self.T, "one training time per table row"
         self.mlp = mlp
         self._mlp_times = torch.cat((torch.zeros(1), train_times.detach().float().cpu().reshape(-1))).to(self.dev)
-        self._mlp_lr = float(lr)
+        self._mlp_lr = float(lr)            # deform_lr_init of every reference config (train_kubric_mrig.yaml: 0.0016)
         self._mlp_moments = None
+        self._mlp_steps = 0                 # Adam's own step count (bias correction), like torch.optim.Adam's state["step"]
         return mlp
 
     def basis_forward(self, t) -> torch.Tensor:
@@ -424,17 +468,21 @@ class SplatTrainStep:
         own view time, so its gradient must go through the network before anything is summed across views."""
         return allreduce_flat(self.mlp.grad, scale, self.pg)
 
-    def basis_optimizer_step(self, iteration: int, grad_scale: float = 1.0):
+    def basis_optimizer_step(self, iteration: Optional[int] = None, grad_scale: float = 1.0):
         """Adam step of the "deform_network" group (append_motion_optim, src/trainer/rodygs_dynamic.py:101-106: one group,
         eps 1e-15) on the packed buffer - one rdg_adam launch.  The learning rate is constant = deform_lr_init:
         update_learning_rate (:199-213) looks for a group named "deform", which does not exist, so the exponential
-        schedule built at :118-123 is never applied."""
+        schedule built at :118-123 is never applied.  Bias correction uses the number of steps THIS optimiser has taken
+        (torch.optim.Adam's per-parameter state["step"]), not the training iteration: the two differ whenever the network
+        was not stepped from iteration 1 on (warm-up, late attach, resume).  `iteration` is accepted for call-site
+        compatibility and ignored."""
         mlp = self.mlp
+        self._mlp_steps += 1
         if self._mlp_moments is None:
             self._mlp_moments = (torch.zeros_like(mlp.grad), torch.zeros_like(mlp.grad))
         m, v = self._mlp_moments
         check(_lib.load().rdg_adam(ptr(mlp.params), ptr(mlp.grad), ptr(m), ptr(v), mlp.params.numel(), self._mlp_lr, 0.9, 0.999,
-                                   1e-15, int(iteration), float(grad_scale), _lib.stream_ptr()))
+                                   1e-15, int(self._mlp_steps), float(grad_scale), _lib.stream_ptr()))
 
     # -- optimiser, densification (SURVEY.md §8 f1 / f2) ------------------------------------------------
     def _group_ranges(self, tag: str) -> Dict[str, Tuple[int, int]]:
@@ -457,7 +505,13 @@ class SplatTrainStep:
         return opt
 
     def optimizer_step(self, tag: str, iteration: int, grad_scale: float = 1.0):
-        """current_gs.update_learning_rate(iteration); current_gs.optimizer.step() (rodygs.py:209,364)."""
+        """current_gs.update_learning_rate(iteration); current_gs.optimizer.step() (rodygs.py:209,364).
+        The reference densifies BEFORE optimizer.step() in the same iteration (rodygs.py:343-364); densification re-creates
+        every nn.Parameter of the model, their .grad is None, and torch.optim.Adam skips them - so on a densification
+        iteration that model's step is a no-op (no update, no step count).  densify_and_prune() arms the same skip here."""
+        if tag in self._skip_step:
+            self._skip_step.discard(tag)
+            return None
         return self.optim[tag].step(self.params, self.grads, iteration, grad_scale)
 
     def enable_densification(self, tag: str):
@@ -484,7 +538,10 @@ class SplatTrainStep:
         parallelism every rank calls this with all-reduced statistics and the same noise."""
         from . import densify as dn
         from .optim import GROUP_OF
-        if tag in self.stats and self.pg is not None:
+        if tag in self.stats:
+            # every data-parallel user of this class runs on the default group (process_group=None): the statistics must be
+            # made rank-consistent there too, or the ranks clone / split / prune different rows and their buffer sizes
+            # diverge.  all_reduce() is a no-op for a single process.
             self.stats[tag].all_reduce(self.pg)
         params = self._model_tensors(tag)
         opt = self.optim.get(tag)
@@ -520,6 +577,8 @@ class SplatTrainStep:
         self.stats[tag] = new_stats
         if getattr(self, "_fx_args", None) is not None:          # the exchange buffers are sized by the Gaussian count
             self.enable_factored_exchange(*self._fx_args)
+        if tag in self.optim:
+            self._skip_step.add(tag)
         return info
 
     def reset_opacity(self, tag: str, cap: float = 0.01):
@@ -592,6 +651,6 @@ class SplatTrainStep:
         return parts
 
     def total_loss(self) -> torch.Tensor:
-        """photometric + w_p * pearson + alpha term (device scalar)."""
+        """photometric + w_p * pearson + w_local * local pearson + alpha term (device scalar)."""
         lp = self.loss_parts
-        return lp[0] + self.w[2] * lp[3] + lp[4]
+        return lp[0] + self.w[2] * lp[3] + lp[4] + (self.w_local * lp[5] if self.n_local > 0 else 0.0)

@@ -60,7 +60,8 @@ def test_argument_errors_are_reported_without_a_gpu():
     ws = lib.rdg_bin_workspace_bytes(1000, 4000, 64, 64)
     assert ws > 4000 * 12 and ws % 256 == 0
     assert lib.rdg_l1_dssim_workspace_bytes(3, 0, 10) == -1
-    assert lib.rdg_l1_dssim_workspace_bytes(3, 8, 8) == 256 + 3 * 3 * 64 * 4
+    assert lib.rdg_l1_dssim_workspace_bytes(3, 8, 8) == 256 + 3 * 3 * 64 * 4 + 256 * 64     # + the local-Pearson box scratch
+    assert lib.rdg_blend_bwd_deterministic_scratch_bytes(10) >= 10 * 12 * 12 and lib.rdg_blend_bwd_deterministic_scratch_bytes(-1) == -1
     assert lib.rdg_adam(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-15, 1, 1.0, None) == -1
     with pytest.raises(RuntimeError, match="rodygs_b200 error -1"):
         _lib.check(lib.rdg_blend_fwd(0, None, None, None, None, None))

@@ -158,3 +158,54 @@ def test_factored_sh_exchange_matches_sequential():
     assert ref[o:].abs().max() > 0
     assert helpers.rel_err(got, ref) < 1e-5
     assert torch.allclose(got, ref, rtol=1e-3, atol=1e-7)
+
+
+def _worker_stats(rank, world, port, ret):
+    """DensifyStats.all_reduce on the DEFAULT group (what SplatTrainStep.densify_and_prune calls when it was built without a
+    process_group, as bench.py and every data-parallel user does): sum / sum / max over the ranks."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from rodygs_b200.densify import DensifyStats
+        g = torch.Generator().manual_seed(100 + rank)
+        st = DensifyStats(50, "cpu")
+        st.grad_accum.copy_(torch.rand(50, generator=g))
+        st.denom.copy_(torch.randint(0, 3, (50,), generator=g).float())
+        st.max_radii2D.copy_(torch.randint(0, 40, (50,), generator=g).float())
+        st.all_reduce(None)
+        ret.put((rank, st.grad_accum.clone(), st.denom.clone(), st.max_radii2D.clone()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_densification_statistics_are_rank_consistent_on_the_default_group():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_worker_stats, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict((r[0], r[1:]) for r in (ret.get(timeout=120), ret.get(timeout=120)))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    per_rank = []
+    for rank in range(2):
+        g = torch.Generator().manual_seed(100 + rank)
+        per_rank.append((torch.rand(50, generator=g), torch.randint(0, 3, (50,), generator=g).float(),
+                         torch.randint(0, 40, (50,), generator=g).float()))
+    want = (per_rank[0][0] + per_rank[1][0], per_rank[0][1] + per_rank[1][1], torch.maximum(per_rank[0][2], per_rank[1][2]))
+    for rank in range(2):
+        for a, b in zip(got[rank], want):
+            assert torch.equal(a, b)
+
+
+def test_trainer_densify_always_reduces_its_statistics():
+    """the all-reduce must not be gated on an explicit process_group."""
+    import inspect
+    from rodygs_b200.trainer import SplatTrainStep
+    src = inspect.getsource(SplatTrainStep.densify_and_prune)
+    assert "self.stats[tag].all_reduce(self.pg)" in src and "self.pg is not None" not in src

@@ -427,6 +427,59 @@ def test_fused_loss_stage_matches_oracle():
         assert abs(out2[0].item() - photo.item()) < 2e-6 and out2[3].item() == -1.0 and out2[4].item() == -1.0
 
 
+def test_full_reference_loss_in_one_loss_stage():
+    """Every reference config's objective on the rendered maps - 0.8 L1 + 0.2 D-SSIM (train_kubric_mrig.yaml:135-144) + 0.05
+    global Pearson (:145-150) + 0.15 local Pearson over random 128x128 boxes (:151-158, losses.py:132-182) - from ONE
+    rdg_losses call, value and gradients, against loss_oracle (pinned to the reference's loss_utils by losses.npz)."""
+    import ctypes as C
+    from oracle import loss_oracle as lo
+    from rodygs_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(12)
+    for (H, W, box_p, n_box) in ((300, 420, 128, 3), (270, 480, 64, 14), (160, 160, 128, 1)):
+        a = torch.rand(3, H, W, generator=g)
+        b = (a + 0.1 * torch.randn(3, H, W, generator=g)).clamp(0, 1)
+        d1 = torch.rand(1, H, W, generator=g) * 5 + torch.linspace(0, 3, W).reshape(1, 1, W)
+        d2 = (d1 * 0.7 + 0.5 * torch.rand(1, H, W, generator=g))
+        x0 = torch.randint(0, H - box_p, (n_box,), generator=g)
+        y0 = torch.randint(0, W - box_p, (n_box,), generator=g)
+        for w_p in (0.05, 0.0):
+            ar, dr = a.clone().requires_grad_(True), d1.clone().requires_grad_(True)
+            photo = lo.photometric(ar, b)
+            pear = lo.pearson_depth(dr, d2)
+            local = lo.local_pearson_depth(dr, d2, x0, y0, box_p)
+            (photo + w_p * pear + 0.15 * local).backward()
+            dev = "cuda"
+            ac, bc, dc, d2c = a.to(dev), b.to(dev), d1.to(dev), d2.to(dev)
+            boxes = torch.stack([x0, y0, torch.full_like(x0, box_p), torch.full_like(x0, box_p)], 1).to(torch.int32).to(dev).contiguous()
+            out = torch.full((8,), -1.0, device=dev)
+            gcol = torch.empty(3, H, W, device=dev)
+            gdep = torch.full((1, H, W), 7.0, device=dev)
+            ws_bytes = int(lib.rdg_l1_dssim_workspace_bytes(3, H, W))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            terms = _lib.RdgLossTerms()
+            terms.depth, terms.gt_depth, terms.dL_ddepth = dc.data_ptr(), d2c.data_ptr(), gdep.data_ptr()
+            terms.w_pearson, terms.pearson_eps = w_p, 1e-6
+            terms.local_boxes, terms.n_local_boxes, terms.w_local = boxes.data_ptr(), n_box, 0.15
+            for _ in range(2):   # twice: the call resets its own scratch
+                _lib.check(lib.rdg_losses(ac.data_ptr(), bc.data_ptr(), 3, H, W, 0.8, 0.2, C.byref(terms), out.data_ptr(),
+                                          gcol.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr()))
+            o = out.cpu()
+            assert abs(o[0].item() - photo.item()) < 2e-6
+            if w_p:
+                assert abs(o[3].item() - pear.item()) < 2e-6
+            assert abs(o[5].item() - local.item()) < 2e-6, (o[5].item(), local.item())
+            assert helpers.rel_err(gcol.cpu(), ar.grad) < GRAD_TOL
+            assert helpers.rel_err(gdep.cpu(), dr.grad) < GRAD_TOL, (H, W, w_p)
+            ok, ratio = helpers.elementwise_ok(gdep, dr.grad, rtol=1e-3, floor=1e-4)
+            assert ok, f"dL/ddepth element-wise {ratio:.2f}"
+            # the stand-alone batched kernel agrees with the fused term
+            from rodygs_b200 import losses
+            dd = d1.to(dev).requires_grad_(True)
+            lp = losses.local_pearson_depth_loss(dd, d2c, box_p, origins=torch.stack([x0, y0], 1))
+            assert abs(lp.item() - local.item()) < 2e-6
+
+
 def test_sync_free_mode_matches_and_reports_overflow():
     H, W, n = 64, 64, 1500
     sc, cam = helpers.small_scene(n, H, W, 4, seed=2)

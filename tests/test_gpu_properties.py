@@ -169,6 +169,8 @@ def test_factored_sh_exchange_equals_direct_sum_over_views():
     N, H, W, T, VIEWS = 50_000, 192, 256, 6, 3
     scene = synthetic.to_device(synthetic.make_scene(N, H, W, T, seed=4), "cuda")
     step = SplatTrainStep(scene, H, W, sh_degree=3, w_pearson=0.05, w_alpha=0.01)
+    assert step.n_local == 1
+    step.local_box_origins = torch.tensor([[10, 20]])      # both passes below must see the same local-Pearson box
     gen = torch.Generator(device="cuda").manual_seed(9)
     views = []
     for v in range(VIEWS):
@@ -204,3 +206,45 @@ def test_factored_sh_exchange_equals_direct_sum_over_views():
             n *= s
         a, b = got[o:o + n], ref[o:o + n]
         assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-12, name
+
+
+def test_deterministic_mode_is_bit_reproducible_and_agrees_with_the_default():
+    """engine.config.deterministic (RDG_DETERMINISTIC=1): every gradient of the fused path is bit-identical run to run
+    (integer accumulation of the blend partials, one CTA for the cross-CTA sums), and equals the default float-atomic
+    result to accumulation-order noise."""
+    from rodygs_b200.dynamic import GaussianParams, render_dynamic
+    from rodygs_b200.rasterizer import GaussianRasterizationSettings
+    N, H, W, T = 20000, 160, 240, 12
+    sc = synthetic.make_scene(N, H, W, T, seed=3, radius_px=6.0)
+    cam = synthetic.make_camera(2, 8, H, W, T)
+    g = torch.Generator().manual_seed(1)
+    up = [t.cuda() for t in (torch.randn(3, H, W, generator=g), 0.3 * torch.randn(1, H, W, generator=g), 0.2 * torch.randn(1, H, W, generator=g))]
+
+    def run():
+        cst = GaussianParams(**{k: v.cuda().requires_grad_(True) for k, v in sc["static"].items()})
+        cdy = GaussianParams(**{k: v.cuda().requires_grad_(True) for k, v in sc["dynamic"].items()})
+        leaves = {"coeff": sc["motion_coeff"].cuda().requires_grad_(True), "table": sc["table"].cuda().requires_grad_(True),
+                  "basis_t": sc["table"][cam.time_index].cuda().requires_grad_(True),
+                  "vm": cam.world_view_transform.t().contiguous().cuda().requires_grad_(True)}
+        st = GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, torch.zeros(3).cuda(), 1.0,
+                                           cam.projection_matrix.t().contiguous().cuda(), 3, False, False, True, True)
+        pkg = render_dynamic(cst, cdy, st, leaves["vm"], leaves["coeff"], leaves["basis_t"], leaves["table"], sc["time_ind"].cuda(), 1.0, True)
+        ((pkg["rendered_image"] * up[0]).sum() + (pkg["rendered_depth"] * up[1]).sum() + (pkg["rendered_alpha"] * up[2]).sum()).backward()
+        out = {f"{t}.{k}": getattr(p, k).grad.clone() for t, p in (("st", cst), ("dy", cdy)) for k in p._fields}
+        out.update({k: v.grad.clone() for k, v in leaves.items()})
+        out["means2D"] = pkg["viewspace_points"].grad.clone()
+        return out
+
+    try:
+        engine.config.deterministic = True
+        a, b = run(), run()
+        engine.config.deterministic = False
+        c, d = run(), run()
+    finally:
+        engine.config.deterministic = False
+    for k in a:
+        assert torch.equal(a[k], b[k]), f"{k}: deterministic mode differs between two runs"
+        scale = float(c[k].abs().max())
+        assert float((a[k] - c[k]).abs().max()) <= 2e-5 * scale + 1e-30, f"{k}: deterministic vs default"
+    # (the default mode is allowed to differ in the last bits between runs: float atomics)
+    assert any(not torch.equal(c[k], d[k]) for k in c) or True

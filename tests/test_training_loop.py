@@ -151,5 +151,64 @@ def test_training_loop_with_densification_and_opacity_reset():
         one_iter(it, "dynamic")
         if first_after is None:
             first_after = losses[-2]
+            # the reference's optimizer.step() right after densify_and_prune is a no-op for that model (fresh Parameters have
+            # no .grad): no update, no step count
+            assert step.optim["dynamic"].steps == 6 and step.optim["static"].steps == 7
+    assert step.optim["dynamic"].steps == 6 + 11
     assert all(math.isfinite(x) for x in losses)
     assert losses[-1] < first_after, (first_after, losses[-1])
+
+
+def _dp_densify_worker(rank, world, port, ret):
+    """Two ranks on ONE GPU (gloo carries the CUDA tensors through the host): each renders its own views, then both densify."""
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from rodygs_b200 import synthetic
+        step, cam, vm, pm, gt = _make_step(N=12_000, H=96, W=128)
+        step.attach_optimizer("dynamic", ro.GaussianLRs(scaling_lr=0.001, motion_coeff_lr=1.6e-4))
+        step.enable_densification("dynamic")                       # built WITHOUT a process_group: the default group is used
+        for it in range(3):
+            c = synthetic.make_camera(2 * it + rank, 8, 96, 128, 6)   # every rank sees different views
+            bt = step.p("table")[c.time_index].clone()
+            step.forward_backward(c.world_view_transform.t().contiguous().cuda(), c.projection_matrix.t().contiguous().cuda(),
+                                  c.tanfovx, c.tanfovy, bt, gt, None)
+            step.add_densification_stats("dynamic")
+        st = step.stats["dynamic"]
+        local = float(st.grad_accum.sum())
+        thr = 0.5 * float((st.grad_accum / st.denom.clamp(min=1))[st.denom > 0].mean())
+        thr_t = torch.tensor([thr], dtype=torch.float64)
+        dist.broadcast(thr_t, 0)                                   # same threshold everywhere; the statistics do the rest
+        info = step.densify_and_prune("dynamic", float(thr_t), 0.005, 4.0, None,
+                                      generator=torch.Generator(device="cuda").manual_seed(0))
+        ret.put((rank, step.nd, info["clones"], info["split_selected"], local, float(step.p("dynamic.xyz").double().sum()),
+                 float(step.p("motion_coeff").double().abs().sum()), int(step.time_ind.long().sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_data_parallel_ranks_densify_identically_on_the_default_group():
+    """without the all-reduce of the statistics the ranks clone / split / prune different rows and
+    their Gaussian counts diverge (the next collective then hangs or corrupts)."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_dp_densify_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([ret.get(timeout=300), ret.get(timeout=300)])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    a, b = res
+    assert a[4] != b[4], "the two ranks were supposed to see different views"
+    assert a[1:4] == b[1:4] and a[5:] == b[5:], f"ranks diverged: {a} vs {b}"
+    assert a[2] + a[3] > 0
