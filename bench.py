@@ -15,8 +15,12 @@ is not part of BASELINE.json's metric ("raster fwd+bwd+loss"); `--adam` adds the
            timed region.
 `roofline`: the dominant kernel (largest share of the step, timed with CUDA events on the
            launching stream inside the timed region) against MEASURED_PEAKS.json.
-`cpu_baseline` / `--impl reference`: the PyTorch-CPU oracle (oracle/) on BASELINE config 1
-           (10K Gaussians, 256x256, 8 frames), scaled to this workload by algorithmic bytes.
+`e2e_dropin`: the same step through the ZERO-CHANGE integration a RoDyGS user gets by pointing `diff_gauss_pose` at this
+           repo: activated + concatenated tensors -> GaussianRasterizer (autograd Function, per-call allocation, the host
+           read of num_rendered) -> rodygs_b200.losses -> loss.backward(), host-fed like `e2e`.
+`cpu_baseline` / `--impl reference`: the PyTorch-CPU oracle (oracle/) on a bounded sample of the workload - a 256x256
+           window at the workload's Gaussian density per tile - extrapolated to the full workload by algorithmic bytes
+           (`"extrapolated": true`; `steps` / `warmup` are the frames actually run).
 """
 from __future__ import annotations
 
@@ -33,8 +37,18 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-METRIC = "train iters/sec (raster fwd+bwd+loss) at 1080p/2M Gaussians; % HBM roofline"
 UNIT = "it/s"
+
+
+def metric_name(cfg: str, forward_only: bool = False) -> str:
+    """BASELINE.json's metric string for its quoted configuration (c4); the other configs name their own shape."""
+    from rodygs_b200 import synthetic
+    N, H, W, T, _ = synthetic.CONFIGS[cfg]
+    shape = "1080p" if (H, W) == (1080, 1920) else f"{W}x{H}"
+    n = f"{N / 1e6:g}M" if N >= 1_000_000 else f"{N // 1000}K"
+    if forward_only:
+        return f"forward-only render frames/sec at {shape}/{n} Gaussians; % HBM roofline"
+    return f"train iters/sec (raster fwd+bwd+loss) at {shape}/{n} Gaussians; % HBM roofline"
 
 
 def load_peaks():
@@ -49,7 +63,8 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled every 20 ms from before the warm-up; stop(t0, t1) reports the samples
+    that arrived DURING the timed region [t0, t1] (time.time() stamps)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -61,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.idx), "-lms", "20"], stdout=subprocess.PIPE, text=True, bufsize=1)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -69,62 +84,96 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0: float = 0.0, t1: float = float("inf")):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             pass
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(lines):
+            sm, mx, reasons = [], [], set()
+            for _, ln in lines:
+                parts = [p.strip() for p in ln.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+        inside = [ln for ln in self.lines if t0 - 0.02 <= ln[0] <= t1 + 0.03]
+        sm, mx, reasons = parse(inside)
+        where = "timed region"
+        if not sm:                       # a region shorter than the sampling period: fall back to the whole run (warm-up included)
+            sm, mx, reasons = parse(self.lines)
+            where = "whole run (no sample fell inside the timed region)"
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "period_ms": 20, "window": where}
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_rate(cfg: str = "c4_iphone", max_frames: int = 4):
-    """PyTorch-CPU oracle on a bounded sample of workload `cfg`: a 256x256-pixel window (256 tiles) with the workload's own
-    number of Gaussians per tile (N' = N * 256 / tiles - the scene generator draws scales for a fixed screen radius, so the
-    per-tile list length, which is what the blend cost depends on, matches: 737 entries per tile against 723 at BASELINE
-    config 4), same T, same SH degree, same loss terms.  BASELINE config 1 is its own sample.
-    Returns (it/s at the sample, description, algorithmic bytes per iteration of the sample)."""
+def sample_shape(cfg: str):
+    """The bounded CPU sample of workload `cfg`: a 256x256-pixel window (256 tiles) with the workload's own number of
+    Gaussians per tile (N' = N * 256 / tiles - the scene generator draws scales for a fixed screen radius, so the per-tile
+    list length, which is what the blend cost depends on, matches: 736 entries per tile against 723 at BASELINE config 4),
+    same T, same SH degree, same loss terms.  BASELINE config 1 (10K Gaussians, 256x256, CPU-sized) is its own sample."""
+    from rodygs_b200 import synthetic
+    Nf, Hf, Wf, T, _ = synthetic.CONFIGS[cfg]
+    tiles_f = ((Hf + 15) // 16) * ((Wf + 15) // 16)
+    if cfg == "c1_cpu":
+        return Nf, Hf, Wf, T, tiles_f
+    return max(1000, int(round(Nf * 256 / tiles_f))), 256, 256, T, tiles_f
+
+
+def workload_counts(cfg: str, sh_degree: int = 3):
+    """(N, visible V, dynamic N_d, duplicates D, pixels P) of the FULL workload's first view, counted on the CPU with the
+    oracle's preprocess (radii > 0, sum of tiles_touched; bit-exact with the CUDA path by the parity contract) - what the
+    sample's rate is extrapolated with, instead of assumed ratios."""
+    from oracle import deform_oracle as do, splat_oracle as so
+    from rodygs_b200 import synthetic
+    N, H, W, T, _ = synthetic.CONFIGS[cfg]
+    with torch.no_grad():
+        sc = synthetic.make_scene(N, H, W, T, seed=0)
+        cam = synthetic.make_camera(0, 8, H, W, T)
+        st, dy = do.RawGaussians(**sc["static"]), do.RawGaussians(**sc["dynamic"])
+        xyz, op, scl, rot, feat = do.assemble(st, dy, sc["motion_coeff"].squeeze(1), sc["table"][cam.time_index], sc["table"],
+                                              sc["time_ind"].long(), 1.0, True)
+        settings = so.Settings(H, W, cam.tanfovx, cam.tanfovy, torch.zeros(3), 1.0, cam.projection_matrix.t().contiguous(), 0)
+        pp = so.preprocess(xyz, scl, rot, op, feat[:, :1].contiguous(), None, cam.world_view_transform.t().contiguous(), settings)
+    return N, int((pp.radii > 0).sum()), N // 2, int(pp.tiles_touched.long().sum()), H * W
+
+
+def cpu_oracle_rate(cfg: str = "c4_iphone", frames: int = 3, warmup: int = 1, sh_degree: int = 3, w_local: float = 0.15):
+    """PyTorch-CPU oracle (fwd + full reference loss + bwd, all host threads) on `frames` frames of sample_shape(cfg).
+    Returns (it/s at the sample, description, algorithmic bytes per iteration of the sample, per-frame seconds)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle import deform_oracle as do, loss_oracle as lo, splat_oracle as so
     from rodygs_b200 import synthetic
     torch.set_num_threads(os.cpu_count() or 1)
-    Nf, Hf, Wf, T, _ = synthetic.CONFIGS[cfg]
-    tiles_f = ((Hf + 15) // 16) * ((Wf + 15) // 16)
-    if cfg == "c1_cpu":
-        N, H, W = Nf, Hf, Wf
-    else:
-        H = W = 256
-        N = max(1000, int(round(Nf * 256 / tiles_f)))
+    N, H, W, T, tiles_f = sample_shape(cfg)
     sc = synthetic.make_scene(N, H, W, T, seed=0)
     g = torch.Generator().manual_seed(99)
     gt = torch.rand(3, H, W, generator=g)
     gt_d = torch.rand(1, H, W, generator=g)
+    n_box = int(0.5 * (H // 128) * (W // 128))
+    w_alpha = 0.01 if cfg == "c4_iphone" else 0.0
     times, stats = [], None
-    for f in range(-1, max_frames):          # frame -1 = warm-up
-        cam = synthetic.make_camera(max(f, 0), 8, H, W, T)
+    for f in range(-warmup, frames):          # negative frames = warm-up
+        cam = synthetic.make_camera(max(f, 0) % 8, 8, H, W, T)
         t0 = time.perf_counter()
         st = do.RawGaussians(**{k: x.clone().requires_grad_(True) for k, x in sc["static"].items()})
         dy = do.RawGaussians(**{k: x.clone().requires_grad_(True) for k, x in sc["dynamic"].items()})
@@ -134,36 +183,53 @@ def cpu_oracle_rate(cfg: str = "c4_iphone", max_frames: int = 4):
                                               sc["time_ind"].long(), 1.0, True)
         vm = cam.world_view_transform.t().contiguous().requires_grad_(True)
         settings = so.Settings(H, W, cam.tanfovx, cam.tanfovy, torch.zeros(3), 1.0,
-                               cam.projection_matrix.t().contiguous(), 3)
+                               cam.projection_matrix.t().contiguous(), sh_degree)
         out = so.rasterize(xyz, torch.zeros(N, 3, requires_grad=True), feat, None, op, scl, rot, vm, settings)
-        loss = lo.photometric(out.color, gt) + 0.05 * lo.pearson_depth(out.depth, gt_d) + 0.01 * (1 - out.alpha).mean()
+        loss = lo.photometric(out.color, gt) + 0.05 * lo.pearson_depth(out.depth, gt_d) + w_alpha * (1 - out.alpha).mean()
+        if n_box > 0 and w_local:
+            x0 = torch.randint(0, H - 128, (n_box,), generator=g)
+            y0 = torch.randint(0, W - 128, (n_box,), generator=g)
+            loss = loss + w_local * lo.local_pearson_depth(out.depth, gt_d, x0, y0, 128)
         loss.backward()
         dt = time.perf_counter() - t0
         if f >= 0:
             times.append(dt)
             stats = (N, int((out.radii > 0).sum()), N // 2, int(out.bn.keys.numel()), H * W)
     rate = len(times) / sum(times)
-    nbytes = synthetic.algorithmic_bytes(*stats)
+    K = (sh_degree + 1) ** 2
+    nbytes = synthetic.algorithmic_bytes(*stats, sh_coeffs=K)
     desc = (f"oracle (PyTorch-CPU, fp32) on a {256 / tiles_f:.4f} sample of {cfg} at the same Gaussian density per tile: {N} "
             f"Gaussians (50% dynamic), {H}x{W} window ({(H // 16) * (W // 16)} of {tiles_f} tiles, {stats[3] / ((H // 16) * (W // 16)):.0f} "
-            f"list entries per tile), T={T}, {len(times)} frames fwd+loss+bwd after 1 warm-up frame; {rate:.3f} it/s at that size")
-    return rate, desc, nbytes
+            f"list entries per tile), T={T}, SH degree {sh_degree}, {len(times)} frames fwd+loss+bwd after {warmup} warm-up frame(s); "
+            f"{rate:.3f} it/s at that size")
+    return rate, desc, nbytes, times
 
 
 def run_reference(args, rank):
+    """The reference arm: the oracle port on the host cores.  One step = one frame of the bounded sample; the frames actually
+    run are reported as `steps` / `warmup` (at most 24 + 2, so that the arm ends within a few minutes whatever K the driver
+    asks for), and the rate is extrapolated to the full workload by algorithmic bytes with the workload's own counts."""
     if rank != 0:
         return
     from rodygs_b200 import synthetic
-    rate, desc, sample_bytes = cpu_oracle_rate(args.config, max(2, min(4, args.steps)))
-    N, H, W, T, _ = synthetic.CONFIGS[args.config]
-    full_bytes = synthetic.algorithmic_bytes(N, int(0.9 * N), N // 2, 3 * N, H * W)
+    frames, warm = max(1, min(args.steps, 24)), max(1, min(args.warmup, 2))
+    rate, desc, sample_bytes, times = cpu_oracle_rate(args.config, frames, warm, args.sh_degree)
+    counts = workload_counts(args.config, args.sh_degree)
+    full_bytes = synthetic.algorithmic_bytes(*counts, sh_coeffs=(args.sh_degree + 1) ** 2)
     value = rate * sample_bytes / full_bytes
     cores = torch.get_num_threads()
+    ts = sorted(times)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.config), "note": "CPU arm: 256x256-pixel window at the workload's Gaussian density per tile, scaled by algorithmic bytes"},
+        "impl": "reference", "metric": metric_name(args.config), "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": frames, "warmup": warm, "requested_steps": args.steps, "requested_warmup": args.warmup,
+        "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "extrapolated": True,
+        "config": {"workload": workload_name(args.config, args.sh_degree),
+                   "note": "CPU arm: 256x256-pixel window at the workload's Gaussian density per tile; value = sample rate x "
+                           "(sample algorithmic bytes / workload algorithmic bytes), the workload's V and D counted with the oracle's preprocess",
+                   "workload_counts": dict(zip(("n", "visible", "dynamic", "duplicates", "pixels"), counts))},
+        "sample": {"ms_per_frame_median": 1000.0 * ts[len(ts) // 2], "ms_per_frame_min": 1000.0 * ts[0], "ms_per_frame_max": 1000.0 * ts[-1],
+                   "it_per_s": rate, "algorithmic_bytes": sample_bytes, "workload_algorithmic_bytes": full_bytes},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": desc + f"; scaled by algorithmic bytes {sample_bytes / full_bytes:.3e} to {args.config}",
                          "sample_value": rate},
@@ -173,10 +239,10 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_name(cfg):
+def workload_name(cfg, sh_degree=3):
     from rodygs_b200 import synthetic
     N, H, W, T, views = synthetic.CONFIGS[cfg]
-    return f"{cfg}: {N} Gaussians (50% dynamic), {W}x{H}, T={T}, SH degree 3, 1 camera-time view per GPU per step"
+    return f"{cfg}: {N} Gaussians (50% dynamic), {W}x{H}, T={T}, SH degree {sh_degree}, 1 camera-time view per GPU per step"
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -195,7 +261,8 @@ def run_ours(args, rank, world, local_rank):
     scene_cpu = synthetic.make_scene(N, H, W, T, seed=0)
     scene = synthetic.to_device(scene_cpu, dev)
     w_alpha = 0.01 if args.config in ("c4_iphone",) else 0.0
-    step = SplatTrainStep(scene, H, W, sh_degree=3, w_pearson=0.05, w_alpha=w_alpha, device=dev)
+    step = SplatTrainStep(scene, H, W, sh_degree=args.sh_degree, w_pearson=0.05, w_alpha=w_alpha, device=dev,
+                          w_local=0.0 if args.no_local_pearson else 0.15)
     n_views = max(8, world)
     my_views = [v for v in range(n_views) if v % world == rank] or [rank % n_views]
     cams = [synthetic.make_camera(v, n_views, H, W, T) for v in my_views]
@@ -209,6 +276,7 @@ def run_ours(args, rank, world, local_rank):
 
     # targets: render of a perturbed copy of the scene, depth min-max normalised
     targets = []
+    view_counts = []                  # (visible, duplicates) of every view this rank renders
     with torch.no_grad():
         pert = 0.01 * torch.randn(step.p("static.xyz").shape, generator=torch.Generator().manual_seed(1000)).to(dev)
         step.p("static.xyz").add_(pert)
@@ -216,7 +284,8 @@ def run_ours(args, rank, world, local_rank):
             vm, pm = cam_tensors(cam, dev)
             step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, step.p("table")[cam.time_index].contiguous(),
                                   None, None, forward_only=True)
-            color, depth, alpha, _ = step.last_outputs
+            color, depth, alpha, radii_v = step.last_outputs
+            view_counts.append((int((radii_v > 0).sum().item()), int(step.last_state.num_rendered[0].item())))
             d = depth.clone()
             d = (d - d.min()) / (d.max() - d.min() + 1e-12)
             targets.append((color.clone(), d))
@@ -307,40 +376,57 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n_steps, e2e=False):
+    def timed(n_steps, e2e=False, fn=None):
+        """n_steps steps between barriers; returns (total ms = max over ranks, per-step ms of this rank from one CUDA event
+        per step on the launching stream, wall-clock start / end of the region)."""
+        fn = fn or one_step
         barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps + 1)]
+        t0 = time.time()
+        evs[0].record()
         for k in range(n_steps):
-            one_step(k, e2e)
-        ev1.record()
+            fn(k, e2e)
+            evs[k + 1].record()
         barrier()
-        ms = ev0.elapsed_time(ev1)
+        t1 = time.time()
+        ms = evs[0].elapsed_time(evs[-1])
+        per_step = [evs[k].elapsed_time(evs[k + 1]) for k in range(n_steps)]
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms
+        return ms, per_step, t0, t1
 
-    for k in range(max(args.warmup, 3)):
-        one_step(k)
-    torch.cuda.synchronize()
+    def pct(xs):
+        ys = sorted(xs)
+        q = lambda f: ys[min(len(ys) - 1, int(f * len(ys)))]
+        return {"median": q(0.5), "p10": q(0.1), "p90": q(0.9), "min": ys[0], "max": ys[-1], "n": len(ys)}
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.start()                     # before the warm-up: the 20 ms sampler is up and running when the timed region starts
+    n_warm = max(args.warmup, 3)
+    for k in range(n_warm):
+        one_step(k)
+    torch.cuda.synchronize()
+
     launches0 = int(lib.rdg_launch_count())
     step.enable_stage_timing()
-    ms_total = timed(args.steps)
+    ms_total, per_step, t_region0, t_region1 = timed(args.steps)
     launches = int(lib.rdg_launch_count()) - launches0
     events = step.stage_events
     step.stage_events = None
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_region0, t_region1) if sampler else None
 
     # e2e leg (host buffers -> H2D -> step -> D2H loss)
     for k in range(2):
         one_step(k, e2e=True)
-    ms_e2e = timed(args.steps, e2e=True)
+    ms_e2e, per_step_e2e, _, _ = timed(args.steps, e2e=True)
+
+    # ---- e2e through the drop-in API (zero-change integration): activated tensors -> GaussianRasterizer -> losses -> backward
+    dropin = None
+    if not args.forward_only and not args.no_dropin and world == 1:
+        dropin = run_dropin_leg(args, step, host_inputs, cams, dev, timed, pct)
 
     # ---- the motion-basis MLP (row a1), timed on its own: the scene's table is a stand-in for its output
     # (SURVEY.md §8d), so the network runs beside the step, not inside it ----
@@ -376,12 +462,12 @@ def run_ours(args, rank, world, local_rank):
         prev = ev
     stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
 
-    state = step.last_state
-    D = int(state.num_rendered[0].item())
-    V = int((state.geom["radii"] > 0).sum().item())
+    # algorithmic bytes use the MEAN visible / duplicate counts over the views this rank cycles through
+    V = int(round(sum(c[0] for c in view_counts) / len(view_counts)))
+    D = int(round(sum(c[1] for c in view_counts) / len(view_counts)))
     P = H * W
     nd = step.nd
-    K = 16
+    K = (args.sh_degree + 1) ** 2
     stage_bytes = {
         "preprocess_fwd": 52 * N + (41 + 12 * K) * V + 68 * nd,
         "bin": 8 * N + 20 * V + 44 * D,
@@ -428,17 +514,20 @@ def run_ours(args, rank, world, local_rank):
         e2e_value = world * 1000.0 / (ms_e2e / args.steps)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rate, desc, sample_bytes = cpu_oracle_rate(args.config, 3)
+            rate, desc, sample_bytes, _ = cpu_oracle_rate(args.config, 3, 1, args.sh_degree, 0.0 if args.no_local_pearson else 0.15)
             scaled = rate * sample_bytes / total_bytes
             cpu = {"value": scaled, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                    "sample": desc + f"; scaled by algorithmic bytes ({sample_bytes / total_bytes:.3e}) to this workload",
                    "sample_value": rate}
         line = {
-            "metric": METRIC if not args.forward_only else "forward-only render frames/sec (BASELINE config 5)",
-            "value": value, "unit": UNIT if not args.forward_only else "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": workload_name(args.config), "n_gaussians": N, "visible": V, "duplicates": D,
+            "metric": metric_name(args.config, args.forward_only),
+            "value": value, "unit": UNIT if not args.forward_only else "frames/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+            "ms_per_step": ms_step, "ms_per_step_stats": pct(per_step), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.config, args.sh_degree), "n_gaussians": N, "visible": V, "duplicates": D,
+                       "sh_degree": args.sh_degree,
+                       "loss": ("0.8 L1 + 0.2 D-SSIM + 0.05 global Pearson" + ("" if args.no_local_pearson else f" + 0.15 local Pearson ({step.n_local} boxes of 128x128)")
+                                + (" + 0.01 mean(1 - alpha)" if w_alpha else "")) if not args.forward_only else "none (forward only)",
                        "pixels": P, "views_per_step": world, "l2": "inputs larger than L2 (params+SH 472 MB, sort buffers)",
                        "optimizer": "fused Adam in the timed region" if args.adam else "excluded (metric = raster fwd+bwd+loss)",
                        "sync_free": True, "parallelism": (f"dp{world} (view-sharded; all-gather of the 12 B/Gaussian factors of dL/dSH + allreduce of "
@@ -446,7 +535,9 @@ def run_ours(args, rank, world, local_rank):
                                        f"dp{world} (view-sharded, allreduce of the flat gradient buffer)")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "ms_per_step_stats": pct(per_step_e2e),
+                    "api": "rodygs_b200.trainer.SplatTrainStep.forward_backward (fused flat-buffer path)"},
+            "e2e_dropin": dropin,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -462,11 +553,76 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
 
 
+def run_dropin_leg(args, step, host_inputs, cams, dev, timed, pct):
+    """One training step the way an UNMODIFIED RoDyGS trainer would run it on this library: the activated,
+    concatenated tensors of get_GS_properties (rodygs.py:68-113) -> GaussianRasterizationSettings / GaussianRasterizer
+    (renderer.py:50-101; torch.autograd.Function, per-call allocation, the host read of num_rendered) -> the reference's loss
+    functions from rodygs_b200.losses -> loss.backward().  Host-fed like `e2e`: the view's matrices and targets come from
+    pinned host memory every step and the loss is read back."""
+    from rodygs_b200 import engine, losses
+    from rodygs_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    was = engine.config.sync_free
+    engine.config.sync_free = False          # the drop-in API keeps the reference's one host read per forward
+    try:
+        with torch.no_grad():                # activated + concatenated leaves (static first, dynamic second, no deformation)
+            cat = lambda k: torch.cat([step.p(f"static.{k}"), step.p(f"dynamic.{k}")], 0)
+            xyz = cat("xyz").clone().requires_grad_(True)
+            opac = torch.sigmoid(cat("opacity")).requires_grad_(True)
+            scal = torch.exp(cat("scaling")).requires_grad_(True)
+            rot = torch.nn.functional.normalize(cat("rotation")).requires_grad_(True)
+            feat = torch.cat([cat("features_dc"), cat("features_rest")], 1).contiguous().requires_grad_(True)
+        leaves = [xyz, opac, scal, rot, feat]
+        n = xyz.shape[0]
+        bg = torch.zeros(3, device=dev)
+        slots = [tuple(torch.empty_like(t, device=dev) for t in host_inputs[0][:5]) for _ in range(2)]
+        host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+        H, W = step.H, step.W
+        n_box = step.n_local
+
+        def one(k, e2e=True):
+            hvm, hpm, hbt, hgt, hgtd, cam = host_inputs[k % len(host_inputs)]
+            vm, pm, _, gt, gtd = slots[k % 2]
+            vm.copy_(hvm, non_blocking=True); pm.copy_(hpm, non_blocking=True)
+            gt.copy_(hgt, non_blocking=True); gtd.copy_(hgtd, non_blocking=True)
+            for t in leaves:
+                t.grad = None
+            vm_leaf = vm.clone().requires_grad_(True)
+            means2D = torch.zeros(n, 3, device=dev, requires_grad=True)
+            st = GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, bg, 1.0, pm, args.sh_degree, False, False, True, True)
+            color, depth, normal, alpha, radii, extra = GaussianRasterizer(st)(
+                means3D=xyz, means2D=means2D, shs=feat, colors_precomp=None, opacities=opac, scales=scal, rotations=rot,
+                cov3Ds_precomp=None, viewmatrix=vm_leaf)
+            loss = losses.photometric_loss(color, gt, 0.8, 0.2) + 0.05 * losses.pearson_depth_loss(depth, gtd)
+            if n_box > 0:
+                loss = loss + 0.15 * losses.local_pearson_depth_loss(depth, gtd, 128, 0.5)
+            loss.backward()
+            host_loss.copy_(loss.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        steps = max(5, min(args.steps, 30))
+        for k in range(3):
+            one(k)
+        ms, per_step, _, _ = timed(steps, True, one)
+        h2d = sum(t.numel() * 4 for t in (slots[0][0], slots[0][1], slots[0][3], slots[0][4]))
+        return {"value": 1000.0 * steps / ms, "unit": UNIT, "ms_per_step": ms / steps, "ms_per_step_stats": pct(per_step), "steps": steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + 8,
+                "api": "diff_gauss_pose.GaussianRasterizer (drop-in) + rodygs_b200.losses + autograd; activated, concatenated "
+                       "inputs, no fused deformation, dL/dSH written in full"}
+    finally:
+        engine.config.sync_free = was
+        for t in (xyz, opac, scal, rot, feat):
+            t.grad = None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--sh-degree", type=int, default=3, choices=[0, 1, 2, 3],
+                    help="active SH degree (the reference trains at degree 0 for 15000 of 20000 iterations)")
+    ap.add_argument("--no-local-pearson", action="store_true", help="leave the 0.15-weighted LocalPearsonDepthLoss out of the step (A/B)")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the e2e_dropin leg (GaussianRasterizer + autograd)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c4_iphone")
     ap.add_argument("--n-gaussians", type=int, default=0)

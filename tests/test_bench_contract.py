@@ -22,6 +22,22 @@ def test_reference_arm_prints_the_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "oracle" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+    # honest bookkeeping: the frames actually run, an explicit extrapolation flag, the workload's own counts
+    assert d["extrapolated"] is True and d["warmup"] == 1 and d["requested_steps"] == 2
+    wc = d["config"]["workload_counts"]
+    assert wc["n"] == 10000 and 0 < wc["visible"] <= wc["n"] and wc["duplicates"] >= wc["visible"]
+    assert d["metric"].startswith("train iters/sec (raster fwd+bwd+loss) at 256x256/10K Gaussians")
+
+
+def test_reference_arm_caps_the_frames_it_runs():
+    sys.path.insert(0, ROOT)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert b.metric_name("c4_iphone") == "train iters/sec (raster fwd+bwd+loss) at 1080p/2M Gaussians; % HBM roofline"   # BASELINE.json
+    assert "960x540/1M" in b.metric_name("c3_nvidia") and "512x512/300K" in b.metric_name("c2_kubric")
+    assert b.sample_shape("c4_iphone")[:3] == (62745, 256, 256)
 
 
 def test_cpu_sample_matches_the_workload_density():
