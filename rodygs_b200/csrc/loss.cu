@@ -47,6 +47,25 @@ struct __align__(16) LocalBox {
 };
 static_assert(sizeof(LocalBox) == 64, "LocalBox layout");
 
+// The local Pearson boxes that overlap the 32x32 tile at (tx0, ty0), in box order, into near[] (call from warp 0; ballot
+// compaction, so that per-pixel sums over the list keep one order).  A 128x128 box overlaps ~1 % of the tiles: every thread
+// testing all ~60 boxes itself cost 12 M warp instructions per pass (ncu r02).
+__device__ __forceinline__ int boxes_near_tile(const int4* __restrict__ boxes, int n_boxes, int tx0, int ty0, int* near) {
+    int cnt = 0;
+    for (int base = 0; base < n_boxes; base += 32) {
+        const int b = base + (int)threadIdx.x;
+        bool hit = false;
+        if (b < n_boxes) {
+            const int4 bx = boxes[b];
+            hit = !(bx.x >= ty0 + ST || bx.x + bx.z <= ty0 || bx.y >= tx0 + ST || bx.y + bx.w <= tx0);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) near[cnt + __popc(bal & ((1u << threadIdx.x) - 1u))] = b;
+        cnt += __popc(bal);
+    }
+    return cnt;
+}
+
 // Separable 11-tap blur of an SHL x SHL halo tile down to ST x ST, register-tiled: the horizontal pass
 // gives every thread one row and SEG adjacent outputs (each input is loaded once and used for up to 11
 // taps x NQ planes from registers), the vertical pass one column and VSEG outputs.  12 FMA per shared-memory
@@ -80,9 +99,16 @@ __global__ void __launch_bounds__(LTHREADS) ssim_fwd_kernel(const float* __restr
     __shared__ float in[2][SHL][IPITCH];
     __shared__ float hz[5][SHL][HPITCH];
     __shared__ double red[8][LTHREADS / 32];
+    __shared__ int near_box[LOCAL_BOXES_MAX];
+    __shared__ int n_near_s;
     const int ch = blockIdx.z;
     const size_t plane = (size_t)ch * H * W;
     const int x0 = blockIdx.x * ST - HALO, y0 = blockIdx.y * ST - HALO;
+    const bool local_boxes = ch == 0 && depth && n_boxes > 0;
+    if (local_boxes && threadIdx.x < 32) {                 // (published by the barriers below)
+        const int cnt = boxes_near_tile(boxes, n_boxes, blockIdx.x * ST, blockIdx.y * ST, near_box);
+        if (threadIdx.x == 0) n_near_s = cnt;
+    }
     for (int idx = threadIdx.x; idx < SHL * SHL; idx += LTHREADS) {
         const int r = idx / SHL, c = idx % SHL;
         const int y = y0 + r, x = x0 + c;
@@ -184,11 +210,11 @@ __global__ void __launch_bounds__(LTHREADS) ssim_fwd_kernel(const float* __restr
         atomicAdd(&hdr->sums[threadIdx.x], t);
     }
     // local Pearson boxes that overlap this tile (uniform loop; a 128x128 box overlaps ~1 % of the 32x32 tiles)
-    if (ch == 0 && depth && n_boxes > 0) {
-        const int tx0 = blockIdx.x * ST, ty0 = blockIdx.y * ST;
-        for (int b = 0; b < n_boxes; ++b) {
+    if (local_boxes) {
+        const int n_near = n_near_s;
+        for (int kb = 0; kb < n_near; ++kb) {
+            const int b = near_box[kb];
             const int4 bx = boxes[b];                             // row0, col0, rows, cols
-            if (bx.x >= ty0 + ST || bx.x + bx.z <= ty0 || bx.y >= tx0 + ST || bx.y + bx.w <= tx0) continue;
             double s5[5] = {0, 0, 0, 0, 0};
             const bool xin = x >= bx.y && x < bx.y + bx.w && x < W;
 #pragma unroll
@@ -270,19 +296,7 @@ __global__ void __launch_bounds__(LTHREADS) ssim_bwd_kernel(const float* __restr
     __shared__ int n_near_s;
     if (do_depth && n_boxes > 0) {
         if (threadIdx.x < 32) {
-            const int tx0 = blockIdx.x * ST, ty0 = blockIdx.y * ST;
-            int cnt = 0;
-            for (int base = 0; base < n_boxes; base += 32) {
-                const int b = base + (int)threadIdx.x;
-                bool hit = false;
-                if (b < n_boxes) {
-                    const int4 bx = boxes[b];
-                    hit = !(bx.x >= ty0 + ST || bx.x + bx.z <= ty0 || bx.y >= tx0 + ST || bx.y + bx.w <= tx0);
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, hit);
-                if (hit) near_box[cnt + __popc(bal & ((1u << threadIdx.x) - 1u))] = b;
-                cnt += __popc(bal);
-            }
+            const int cnt = boxes_near_tile(boxes, n_boxes, blockIdx.x * ST, blockIdx.y * ST, near_box);
             if (threadIdx.x == 0) n_near_s = cnt;
         }
         __syncthreads();
