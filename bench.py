@@ -314,7 +314,8 @@ def run_ours(args, rank, world, local_rank):
     factored = world > 1 and not args.plain_allreduce and not args.forward_only
     all_vm, all_bt = [], []
     if factored:
-        step.enable_factored_exchange(views_per_rank=1, world_size=world, copy_engine_gather=not args.nccl_gather)
+        step.enable_factored_exchange(views_per_rank=1, world_size=world, copy_engine_gather=not args.nccl_gather,
+                                      bucketed=not args.no_bucketed, sm_reserve=args.sm_reserve, multicast=args.multicast)
         for j in range(len(my_views)):
             cs = [synthetic.make_camera(r + j * world, n_views, H, W, T) for r in range(world)]
             all_vm.append(torch.stack([c.world_view_transform.t().contiguous() for c in cs]).to(dev).contiguous())
@@ -428,6 +429,25 @@ def run_ours(args, rank, world, local_rank):
     if not args.forward_only and not args.no_dropin and world == 1:
         dropin = run_dropin_leg(args, step, host_inputs, cams, dev, timed, pct)
 
+    # ---- optional per-stream kernel timeline of one step (torch.profiler / CUPTI; never inside the timed region) ----
+    if args.timeline:
+        from torch.profiler import profile, ProfilerActivity
+        barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for k in range(3):
+                one_step(k)
+            torch.cuda.synchronize()
+        if rank == 0:
+            evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
+            starts = [e for e in evs if "preprocess_fwd" in e.name]
+            lo = starts[-1].time_range.start if starts else evs[0].time_range.start
+            with open(args.timeline, "w") as f:
+                f.write(f"# one data-parallel step on rank 0 of {world} (torch.profiler): start us, duration us, kernel\n")
+                for e in evs:
+                    if e.time_range.start >= lo:
+                        f.write(f"{e.time_range.start - lo:9.1f} {e.time_range.end - e.time_range.start:8.1f}  {e.name[:90]}\n")
+        barrier()
+
     # ---- the motion-basis MLP (row a1), timed on its own: the scene's table is a stand-in for its output
     # (SURVEY.md §8d), so the network runs beside the step, not inside it ----
     mlp_info = None
@@ -531,7 +551,8 @@ def run_ours(args, rank, world, local_rank):
                        "pixels": P, "views_per_step": world, "l2": "inputs larger than L2 (params+SH 472 MB, sort buffers)",
                        "optimizer": "fused Adam in the timed region" if args.adam else "excluded (metric = raster fwd+bwd+loss)",
                        "sync_free": True, "parallelism": (f"dp{world} (view-sharded; all-gather of the 12 B/Gaussian factors of dL/dSH + allreduce of "
-                                       "the other gradients, dL/dSH rebuilt per rank)" if factored else
+                                       "the other gradients" + ("" if args.no_bucketed else f" per model under the other model's backward kernel, {args.sm_reserve} SMs left to NCCL") +
+                                       ", dL/dSH rebuilt per rank)" if factored else
                                        f"dp{world} (view-sharded, allreduce of the flat gradient buffer)")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
@@ -631,6 +652,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-gather", action="store_true",
                     help="N>1: gather the dL/dSH factors with NCCL instead of copy-engine pulls over symmetric memory (A/B)")
+    ap.add_argument("--no-bucketed", action="store_true",
+                    help="N>1: one all-reduce of the non-SH range after the whole backward instead of one per model under the other model's kernel (A/B)")
+    ap.add_argument("--multicast", action="store_true",
+                    help="N>1: gather the dL/dSH factors with NVLS multicast stores from the producing kernel instead of copy-engine pushes (A/B; measured slower)")
+    ap.add_argument("--sm-reserve", type=int, default=16,
+                    help="N>1: SMs the persistent backward kernels leave to NCCL while the bucketed all-reduce runs beside them")
+    ap.add_argument("--timeline", default="", help="write the kernel timeline of one step (rank 0, torch.profiler) to this file")
     ap.add_argument("--plain-allreduce", action="store_true",
                     help="N>1: all-reduce the whole flat gradient buffer instead of the factored SH exchange (A/B)")
     args = ap.parse_args()

@@ -155,6 +155,9 @@ typedef struct RdgSceneGrad {
     float* table;            /* [T,num_basis,7] accumulated (+=) */
     float* basis_t;          /* [num_basis,7]   accumulated (+=) */
     float* g7_scratch;       /* [n_dynamic,8] scratch, required when scene.frame_order is set */
+    int32_t models;          /* 0 or 3: both models; 1: the static model only; 2: the dynamic model only (+ dL/dtable, dL/dB(t)).
+                              * The data-parallel step calls rdg_preprocess_bwd once per model so that the all-reduce of the
+                              * first model's gradient range runs under the second model's kernel (viewmatrix accumulates). */
     float* dcolor;           /* optional [N,3]: dL/d(rgb) of every Gaussian after the SH clamp mask (zeros when it is not
                               * visible) - the 12-byte factors from which rdg_sh_grad_views rebuilds dL/dSH of all views
                               * of a data-parallel step; pass st/dy.sh_dc = sh_rest = NULL with it to skip the dSH rows */
@@ -169,6 +172,8 @@ uint64_t rdg_launch_count(void);
  *   "dtable_v1"    1: first version of the dL/dtable reduction
  *   "diff_smem"    1 (default): the preprocess kernels keep B(t) - table rows in shared memory when num_times <= 140;
  *                  0: every dynamic Gaussian gathers its 448-byte table row from global memory
+ *   "sm_reserve"   n > 0: rdg_preprocess_bwd and rdg_sh_grad_views size their persistent grids for 148 - n SMs, leaving the rest
+ *                  to a collective (NCCL) that runs beside them on another stream (their CTAs take the whole register file)
  *   "deterministic" 1: rdg_preprocess_bwd runs its kernels with one CTA so that the cross-CTA float atomics of dL/dV,
  *                  dL/dtable and dL/dB(t) land in a fixed order (test mode, slow; pair it with rdg_blend_bwd_deterministic)
  * Returns RDG_E_ARG for an unknown name. */
@@ -234,6 +239,11 @@ int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, const RdgGeom
 /* The same factors straight from the blend backward's accumulators (acc rows 6..8, clamp mask applied), so that
  * their all-gather can start before rdg_preprocess_bwd runs.  dcolor [N,3]. */
 int rdg_dcolor_from_acc(int64_t n, const float* acc, const uint8_t* clamped, float* dcolor, void* stream);
+/* ... and written through an NVLink-switch MULTICAST mapping of this rank's block of the gathered buffer (symmetric memory:
+ * dcolor_mc = multicast address + block offset, 16-byte aligned): multimem.st replicates every store to all ranks, so the
+ * all-gather of the factors happens inside the kernel that produces them.  The caller orders it with a cross-rank barrier
+ * before the gathered buffer is read.  Needs NVSwitch multicast support (NVLS); use rdg_dcolor_from_acc + copies otherwise. */
+int rdg_dcolor_multicast(int64_t n, const float* acc, const uint8_t* clamped, float* dcolor_mc, void* stream);
 
 int rdg_sh_grad_views(const RdgScene* scene, int32_t sh_degree, int32_t n_views, const float* viewmatrices,
                       const float* basis_ts, const float* dcolor, float scale, const RdgSetGrad* grad_static,

@@ -59,7 +59,7 @@ class RdgSetGrad(C.Structure):
 class RdgSceneGrad(C.Structure):
     _fields_ = [("st", RdgSetGrad), ("dy", RdgSetGrad), ("colors_precomp", c_ptr), ("means2D", c_ptr),
                 ("viewmatrix", c_ptr), ("motion_coeff", c_ptr), ("table", c_ptr), ("basis_t", c_ptr), ("g7_scratch", c_ptr),
-                ("dcolor", c_ptr)]
+                ("models", C.c_int32), ("dcolor", c_ptr)]
 
 
 class RdgDensifyField(C.Structure):
@@ -114,6 +114,7 @@ SYMBOLS = {
     "rdg_preprocess_bwd": (C.c_int, [C.POINTER(RdgScene), C.POINTER(RdgView), C.POINTER(RdgGeom), c_ptr,
                                      C.POINTER(RdgSceneGrad), c_ptr]),
     "rdg_dcolor_from_acc": (C.c_int, [C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "rdg_dcolor_multicast": (C.c_int, [C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "rdg_sh_grad_views": (C.c_int, [C.POINTER(RdgScene), C.c_int32, C.c_int32, c_ptr, c_ptr, c_ptr, C.c_float,
                                     C.POINTER(RdgSetGrad), C.POINTER(RdgSetGrad), c_ptr]),
     "rdg_l1_dssim_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),

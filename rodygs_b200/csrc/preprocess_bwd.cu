@@ -29,6 +29,7 @@ struct PreBwdParams {
     int use_tma;
     int diff_smem;     // B(t) - table rows staged in shared memory (rdg_stage_diff)
     int dtab_atomic;   // no CSR: accumulate dL/dtable with global atomics from this kernel
+    int64_t c_begin, c_end;   // chunk range of this launch (RdgSceneGrad.models: one model at a time under data parallelism)
 };
 
 template <int DEG>
@@ -108,11 +109,11 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
     };
     int radius_pf = 0;
     unsigned clamped_pf = 0;
-    if ((int64_t)blockIdx.x < cs + cd) {
+    if (p.c_begin + (int64_t)blockIdx.x < p.c_end) {
         int64_t gi;
-        if (chunk_slot(blockIdx.x, gi)) { radius_pf = p.geom.radii[gi]; clamped_pf = p.geom.clamped[gi]; }
+        if (chunk_slot(p.c_begin + blockIdx.x, gi)) { radius_pf = p.geom.radii[gi]; clamped_pf = p.geom.clamped[gi]; }
     }
-    for (int64_t chunk = blockIdx.x; chunk < cs + cd; chunk += gridDim.x) {
+    for (int64_t chunk = p.c_begin + blockIdx.x; chunk < p.c_end; chunk += gridDim.x) {
         const bool dyn = chunk >= cs;
         const RdgSet& set = dyn ? sc.dy : sc.st;
         const RdgSetGrad& gs = dyn ? p.gr.dy : p.gr.st;
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
         const bool vis = radius > 0;
         radius_pf = 0;
         clamped_pf = 0;
-        if (chunk + gridDim.x < cs + cd) {
+        if (chunk + gridDim.x < p.c_end) {
             int64_t gi;
             if (chunk_slot(chunk + gridDim.x, gi)) { radius_pf = p.geom.radii[gi]; clamped_pf = p.geom.clamped[gi]; }
         }
@@ -628,15 +629,23 @@ extern "C" int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, co
         const size_t extra = (size_t)scene->num_times * RDG_DIFF_STRIDE * sizeof(float);
         if (smem + extra <= RDG_PRE_SMEM_MAX) { p.diff_smem = 1; smem += extra; }
     }
-    const int64_t chunks = (scene->n_static + RDG_BLOCK - 1) / RDG_BLOCK + (scene->n_dynamic + RDG_BLOCK - 1) / RDG_BLOCK;
-    const int64_t cap = (int64_t)RDG_SM_COUNT * 2;   // 2 CTAs per SM (register-limited), persistent
+    const int64_t cs_h = (scene->n_static + RDG_BLOCK - 1) / RDG_BLOCK, cd_h = (scene->n_dynamic + RDG_BLOCK - 1) / RDG_BLOCK;
+    const bool do_static = grads->models != 2, do_dynamic = grads->models != 1;
+    p.c_begin = do_static ? 0 : cs_h;
+    p.c_end = do_dynamic ? cs_h + cd_h : cs_h;
+    const int64_t chunks = p.c_end - p.c_begin;
+    if (chunks <= 0) return RDG_OK;
+    // 2 CTAs per SM (register-limited), persistent; "sm_reserve" leaves SMs to a collective running beside this kernel
+    int sms = RDG_SM_COUNT - rdg_tunable(RDG_TUN_SM_RESERVE);
+    if (sms < 8) sms = 8;
+    const int64_t cap = (int64_t)sms * 2;
     const int grid = (int)(chunks < cap ? chunks : cap);
     cudaStream_t s = (cudaStream_t)stream;
     const int rc = scene->raw ? launch_bwd_deg<true>(p, view->sh_degree, grid, smem, s)
                               : launch_bwd_deg<false>(p, view->sh_degree, grid, smem, s);
     if (rc) return rc;
     rdg_count_launches(1);
-    if (csr && grads->table) {
+    if (csr && grads->table && do_dynamic) {
         if (rdg_tunable(RDG_TUN_DTABLE_V1) != 0) {
             const dim3 g(scene->num_times, DT_SLICES);
             dtable_kernel<<<g, 128, 0, s>>>(scene->frame_order, scene->frame_offsets, scene->motion_coeff, grads->g7_scratch,
@@ -646,7 +655,7 @@ extern "C" int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, co
             int slices = (3200 + scene->num_times - 1) / scene->num_times;
             slices = slices < 1 ? 1 : (slices > 32 ? 32 : slices);
             const int64_t items = (int64_t)scene->num_times * slices;
-            int g = (int)(items < RDG_SM_COUNT * 4 ? items : RDG_SM_COUNT * 4);
+            int g = (int)(items < sms * 4 ? items : sms * 4);
             if (rdg_tunable(RDG_TUN_DETERMINISTIC) != 0) g = 1;   // one CTA: the slices of a frame add to dL/dtable in a fixed order
             dtable2_kernel<<<g, 128, 0, s>>>(scene->frame_order, scene->frame_offsets, scene->motion_coeff,
                                              grads->g7_scratch, scene->num_basis, scene->num_times, slices, grads->table,

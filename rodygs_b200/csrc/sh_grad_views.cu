@@ -28,7 +28,9 @@ struct ShGradParams {
     int sh_degree;
     float scale;
     int use_tma;
+    int tab_smem;            // 1: the translation columns of the whole table are staged in shared memory (num_times <= SGV_TAB_MAX_T)
 };
+#define SGV_TAB_MAX_T 144
 
 template <int DEG>
 __global__ void __launch_bounds__(RDG_BLOCK, 2) sh_grad_views_kernel(const ShGradParams p) {
@@ -36,6 +38,8 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) sh_grad_views_kernel(const ShGra
     constexpr int K = (DEG + 1) * (DEG + 1);
     const RdgScene& sc = p.sc;
     float* sh_s = smem;                                   // [256][SH_ROW]
+    float* coef_s = smem + RDG_BLOCK * SH_ROW;            // [256][17]: the chunk's motion coefficients (coalesced load, padded rows)
+    float* tab3_s = coef_s + RDG_BLOCK * 17;              // [T][K][3]: translation columns of the table (tab_smem)
     __shared__ float campos_s[SGV_MAX_VIEWS][3];
     __shared__ float bt3_s[SGV_MAX_VIEWS][RDG_NUM_BASIS_MAX][3];   // B(t_v)[k][0:3]
     const bool deform = sc.raw && sc.use_deform && sc.n_dynamic > 0;
@@ -47,11 +51,19 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) sh_grad_views_kernel(const ShGra
         for (int j = 0; j < 3; ++j)
             campos_s[threadIdx.x][j] = -(vm[j * 4 + 0] * vm[12 + 0] + vm[j * 4 + 1] * vm[12 + 1] + vm[j * 4 + 2] * vm[12 + 2]);
     }
-    if (deform)
+    if (deform) {
         for (int e = threadIdx.x; e < nv * sc.num_basis * 3; e += RDG_BLOCK) {
             const int v = e / (sc.num_basis * 3), r = e - v * sc.num_basis * 3, k = r / 3, j = r - k * 3;
             bt3_s[v][k][j] = p.basis_ts[((int64_t)v * sc.num_basis + k) * 7 + j];
         }
+        // every dynamic Gaussian needs the translation part of its birth-frame row: 48 scattered floats of a 448-byte row per
+        // thread from global memory (the L1TEX-bound gather the preprocess kernels got rid of in round 1) - or 19 KB staged once
+        if (p.tab_smem)
+            for (int e = threadIdx.x; e < sc.num_times * sc.num_basis * 3; e += RDG_BLOCK) {
+                const int row = e / 3, j = e - row * 3;
+                tab3_s[e] = p.sc.table[(int64_t)row * 7 + j];
+            }
+    }
     __syncthreads();
 
     const int64_t N = sc.n_static + sc.n_dynamic;
@@ -68,6 +80,17 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) sh_grad_views_kernel(const ShGra
         const int64_t local = lbase + threadIdx.x;
         const int64_t i = (dyn ? sc.n_static : 0) + local;
 
+        const bool def_chunk = deform && dyn;
+        if (def_chunk) {
+            // coalesced: the chunk's coefficient rows are contiguous in memory; row pitch 17 keeps the per-thread reads conflict-free
+            __syncthreads();                               // the previous chunk is done with coef_s
+            const float* src = sc.motion_coeff + lbase * sc.num_basis;
+            for (int e = threadIdx.x; e < cnt * sc.num_basis; e += RDG_BLOCK) {
+                const int gi = e / sc.num_basis, k = e - gi * sc.num_basis;
+                coef_s[gi * 17 + k] = __ldg(src + e);
+            }
+            __syncthreads();
+        }
         float g[3 * K];
 #pragma unroll
         for (int e = 0; e < 3 * K; ++e) g[e] = 0.f;
@@ -79,45 +102,72 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) sh_grad_views_kernel(const ShGra
             if (def) {
                 // x(t_v) = x - s sum_k c_k B_k(t_i) + s sum_k c_k B_k(t_v): the birth-frame part once, the view part per view
                 const int ti = __ldg(sc.time_ind + local);
-                const float* pc = sc.motion_coeff + local * sc.num_basis;
-                const float* row = sc.table + (int64_t)ti * sc.num_basis * 7;
+                const float* pc = coef_s + threadIdx.x * 17;
                 float bx = 0.f, by = 0.f, bz = 0.f;
+                if (p.tab_smem) {
+                    const float* row = tab3_s + ti * sc.num_basis * 3;
 #pragma unroll
-                for (int k = 0; k < RDG_NUM_BASIS_MAX; ++k) {
-                    c[k] = k < sc.num_basis ? __ldg(pc + k) : 0.f;
-                    if (k < sc.num_basis) {
-                        bx = fmaf(c[k], __ldg(row + k * 7 + 0), bx);
-                        by = fmaf(c[k], __ldg(row + k * 7 + 1), by);
-                        bz = fmaf(c[k], __ldg(row + k * 7 + 2), bz);
+                    for (int k = 0; k < RDG_NUM_BASIS_MAX; ++k) {
+                        c[k] = k < sc.num_basis ? pc[k] : 0.f;
+                        if (k < sc.num_basis) {
+                            bx = fmaf(c[k], row[k * 3 + 0], bx);
+                            by = fmaf(c[k], row[k * 3 + 1], by);
+                            bz = fmaf(c[k], row[k * 3 + 2], bz);
+                        }
+                    }
+                } else {
+                    const float* row = sc.table + (int64_t)ti * sc.num_basis * 7;
+#pragma unroll
+                    for (int k = 0; k < RDG_NUM_BASIS_MAX; ++k) {
+                        c[k] = k < sc.num_basis ? pc[k] : 0.f;
+                        if (k < sc.num_basis) {
+                            bx = fmaf(c[k], __ldg(row + k * 7 + 0), bx);
+                            by = fmaf(c[k], __ldg(row + k * 7 + 1), by);
+                            bz = fmaf(c[k], __ldg(row + k * 7 + 2), bz);
+                        }
                     }
                 }
                 x -= sc.spatial_lr_scale * bx; y -= sc.spatial_lr_scale * by; z -= sc.spatial_lr_scale * bz;
             }
-            for (int v = 0; v < nv; ++v) {
-                const float* d = p.dcolor + ((int64_t)v * N + i) * 3;
-                const float d0 = __ldg(d), d1 = __ldg(d + 1), d2 = __ldg(d + 2);
-                if (d0 == 0.f && d1 == 0.f && d2 == 0.f) continue;     // not visible in view v (or all channels clamped)
-                float vx = x, vy = y, vz = z;
-                if (def) {
-                    float bx = 0.f, by = 0.f, bz = 0.f;
+            // views in groups of four: the twelve factor loads of a group are in flight together (one thread per Gaussian and
+            // 16 warps per SM: with one view's loads at a time the kernel sat in long-scoreboard stalls, ncu r02)
+            for (int v0 = 0; v0 < nv; v0 += 4) {
+                float dcv[4][3];
 #pragma unroll
-                    for (int k = 0; k < RDG_NUM_BASIS_MAX; ++k) {
-                        bx = fmaf(c[k], bt3_s[v][k][0], bx);
-                        by = fmaf(c[k], bt3_s[v][k][1], by);
-                        bz = fmaf(c[k], bt3_s[v][k][2], bz);
-                    }
-                    vx += sc.spatial_lr_scale * bx; vy += sc.spatial_lr_scale * by; vz += sc.spatial_lr_scale * bz;
+                for (int u = 0; u < 4; ++u) {
+                    const bool on = v0 + u < nv;
+                    const float* d = p.dcolor + ((int64_t)(on ? v0 + u : v0) * N + i) * 3;
+                    dcv[u][0] = on ? __ldg(d) : 0.f;
+                    dcv[u][1] = on ? __ldg(d + 1) : 0.f;
+                    dcv[u][2] = on ? __ldg(d + 2) : 0.f;
                 }
-                float dx = vx - campos_s[v][0], dy = vy - campos_s[v][1], dz = vz - campos_s[v][2];
-                const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
-                dx *= inv; dy *= inv; dz *= inv;
-                float b[K];
-                rdg_sh_basis<DEG>(dx, dy, dz, b);
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    g[k * 3 + 0] = fmaf(b[k], d0, g[k * 3 + 0]);
-                    g[k * 3 + 1] = fmaf(b[k], d1, g[k * 3 + 1]);
-                    g[k * 3 + 2] = fmaf(b[k], d2, g[k * 3 + 2]);
+                for (int u = 0; u < 4; ++u) {
+                    const int v = min(v0 + u, nv - 1);
+                    const float d0 = dcv[u][0], d1 = dcv[u][1], d2 = dcv[u][2];
+                    if (d0 == 0.f && d1 == 0.f && d2 == 0.f) continue;     // not visible in view v (or all channels clamped)
+                    float vx = x, vy = y, vz = z;
+                    if (def) {
+                        float bx = 0.f, by = 0.f, bz = 0.f;
+#pragma unroll
+                        for (int k = 0; k < RDG_NUM_BASIS_MAX; ++k) {
+                            bx = fmaf(c[k], bt3_s[v][k][0], bx);
+                            by = fmaf(c[k], bt3_s[v][k][1], by);
+                            bz = fmaf(c[k], bt3_s[v][k][2], bz);
+                        }
+                        vx += sc.spatial_lr_scale * bx; vy += sc.spatial_lr_scale * by; vz += sc.spatial_lr_scale * bz;
+                    }
+                    float dx = vx - campos_s[v][0], dy = vy - campos_s[v][1], dz = vz - campos_s[v][2];
+                    const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+                    dx *= inv; dy *= inv; dz *= inv;
+                    float b[K];
+                    rdg_sh_basis<DEG>(dx, dy, dz, b);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        g[k * 3 + 0] = fmaf(b[k], d0, g[k * 3 + 0]);
+                        g[k * 3 + 1] = fmaf(b[k], d1, g[k * 3 + 1]);
+                        g[k * 3 + 2] = fmaf(b[k], d2, g[k * 3 + 2]);
+                    }
                 }
             }
             if (gs.sh_dc) {
@@ -173,6 +223,60 @@ __global__ void __launch_bounds__(RDG_BLOCK) dcolor_from_acc_kernel(int64_t n, c
     }
 }
 
+// The same factors written straight into EVERY rank's gathered buffer: `dcolor_mc` is the NVLink-switch MULTICAST address
+// (torch symmetric memory, handle.multicast_ptr) of this rank's block, and multimem.st makes the switch replicate each
+// 16-byte store to all GPUs of the group - the all-gather of the data-parallel step fused into the kernel that produces its
+// input: one pass, 24 MB of egress per rank instead of seven 24 MB peer copies queued on the copy engines (0.39 ms at 8
+// GPUs, profiles/r02_timeline_n8_*.txt).  Four Gaussians per thread = three 16-byte multicast stores.
+__device__ __forceinline__ void mc_st_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mc_st_f32(float* addr, float a) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+__global__ void __launch_bounds__(RDG_BLOCK) dcolor_multicast_kernel(int64_t n, const float* __restrict__ acc,
+                                                                     const uint8_t* __restrict__ clamped, float* __restrict__ dcolor_mc) {
+    const int64_t groups = (n + 3) / 4;
+    for (int64_t gq = (int64_t)blockIdx.x * RDG_BLOCK + threadIdx.x; gq < groups; gq += (int64_t)gridDim.x * RDG_BLOCK) {
+        float o[12];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = gq * 4 + u;
+            o[3 * u] = o[3 * u + 1] = o[3 * u + 2] = 0.f;
+            if (i < n) {
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(acc + i * 12 + 4));   // dC, dop, dr, dg
+                const float gb = __ldg(acc + i * 12 + 8);
+                const bool any = g1.z != 0.f || g1.w != 0.f || gb != 0.f;
+                const unsigned cl = any ? clamped[i] : 0u;
+                o[3 * u] = (cl & 1u) ? 0.f : g1.z;
+                o[3 * u + 1] = (cl & 2u) ? 0.f : g1.w;
+                o[3 * u + 2] = (cl & 4u) ? 0.f : gb;
+            }
+        }
+        float* dst = dcolor_mc + gq * 12;
+        if (gq * 4 + 4 <= n) {
+            mc_st_v4(dst, o[0], o[1], o[2], o[3]);
+            mc_st_v4(dst + 4, o[4], o[5], o[6], o[7]);
+            mc_st_v4(dst + 8, o[8], o[9], o[10], o[11]);
+        } else {
+            for (int64_t e = 0; e < (n - gq * 4) * 3; ++e) mc_st_f32(dst + e, o[e]);
+        }
+    }
+    __threadfence_system();
+}
+
+extern "C" int rdg_dcolor_multicast(int64_t n, const float* acc, const uint8_t* clamped, float* dcolor_mc, void* stream) {
+    RDG_CHECK_ARG(acc && clamped && dcolor_mc, "null argument");
+    RDG_CHECK_ARG(((uintptr_t)dcolor_mc & 15u) == 0, "the multicast block must be 16-byte aligned");
+    if (n <= 0) return RDG_OK;
+    const int64_t want = ((n + 3) / 4 + RDG_BLOCK - 1) / RDG_BLOCK;
+    const int grid = (int)(want < (int64_t)RDG_SM_COUNT * 8 ? want : (int64_t)RDG_SM_COUNT * 8);
+    dcolor_multicast_kernel<<<grid, RDG_BLOCK, 0, (cudaStream_t)stream>>>(n, acc, clamped, dcolor_mc);
+    RDG_CHECK_LAUNCH();
+    rdg_count_launches(1);
+    return RDG_OK;
+}
+
 extern "C" int rdg_dcolor_from_acc(int64_t n, const float* acc, const uint8_t* clamped, float* dcolor, void* stream) {
     RDG_CHECK_ARG(acc && clamped && dcolor, "null argument");
     if (n <= 0) return RDG_OK;
@@ -211,11 +315,14 @@ extern "C" int rdg_sh_grad_views(const RdgScene* scene, int32_t sh_degree, int32
     p.viewmats = viewmatrices; p.basis_ts = basis_ts; p.dcolor = dcolor;
     p.n_views = n_views; p.sh_degree = sh_degree; p.scale = scale;
     p.use_tma = ((((uintptr_t)grad_static->sh_rest | (uintptr_t)grad_dynamic->sh_rest) & 15u) == 0) ? 1 : 0;
-    const size_t smem = (size_t)RDG_BLOCK * SH_ROW * sizeof(float);
+    p.tab_smem = (deform && scene->num_times <= SGV_TAB_MAX_T) ? 1 : 0;
+    const size_t smem = ((size_t)RDG_BLOCK * SH_ROW + (size_t)RDG_BLOCK * 17 +
+                         (p.tab_smem ? (size_t)scene->num_times * scene->num_basis * 3 : 0)) * sizeof(float);
     const int64_t chunks = (scene->n_static + RDG_BLOCK - 1) / RDG_BLOCK + (scene->n_dynamic + RDG_BLOCK - 1) / RDG_BLOCK;
-    // persistent grid, two CTAs per SM.  RDG_SGV_SMS (experiments): leave the other SMs to a collective that runs
-    // at the same time - these CTAs take the whole register file of the SMs they sit on.
-    static const int sms = [] { const char* e = getenv("RDG_SGV_SMS"); const int v = e ? atoi(e) : 0; return v > 0 && v <= RDG_SM_COUNT ? v : RDG_SM_COUNT; }();
+    // persistent grid, two CTAs per SM.  "sm_reserve" leaves SMs to a collective that runs at the same time - these CTAs
+    // take the whole register file of the SMs they sit on.
+    int sms = RDG_SM_COUNT - rdg_tunable(RDG_TUN_SM_RESERVE);
+    if (sms < 8) sms = 8;
     const int64_t cap = (int64_t)sms * 2;
     const int grid = (int)(chunks < cap ? chunks : cap);
     cudaStream_t s = (cudaStream_t)stream;

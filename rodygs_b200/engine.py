@@ -372,6 +372,8 @@ class SceneGrads:
     basis_t: Optional[torch.Tensor] = None      # must be zero-initialised
     g7_scratch: Optional[torch.Tensor] = None   # [nd,8] scratch (allocated on demand)
     dcolor: Optional[torch.Tensor] = None       # [N,3] factors of dL/dSH for the data-parallel exchange
+    dcolor_mc: int = 0                          # multicast address of this view's block of the gathered factors (0: none)
+    dcolor_stream: Optional[torch.cuda.Stream] = None   # side stream for the multicast kernel (its stores take NVLink time)
 
 
 def _setgrad_struct(g: SetGrads) -> RdgSetGrad:
@@ -383,10 +385,13 @@ def _setgrad_struct(g: SetGrads) -> RdgSetGrad:
 
 
 def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: SceneGrads, stage_hook=None,
-                    after_blend=None):
+                    after_blend=None, after_model=None):
     """blend backward -> preprocess backward.  Writes into the tensors of `grads`.
     after_blend: data-parallel mode - called as soon as grads.dcolor (the factors of dL/dSH) is final, i.e.
-    right after the blend backward, so that their all-gather overlaps the per-Gaussian backward."""
+    right after the blend backward, so that their all-gather overlaps the per-Gaussian backward.
+    after_model: data-parallel mode - the per-Gaussian backward runs as one launch per model (dynamic first: it is the
+    larger gradient range) and after_model("dynamic") / after_model("static") is called right after each, so that the
+    all-reduce of one model's range runs under the other model's kernel."""
     lib = _lib.load()
     dev = state.view.viewmatrix.device
     stream = _lib.stream_ptr()
@@ -415,7 +420,21 @@ def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: Sce
                                 ptr(dL_dcolor), ptr(dL_ddepth), ptr(dL_dalpha), ptr(acc), stream))
     early = after_blend is not None and grads.dcolor is not None and state.scene.colors_precomp is None
     if early:
-        check(lib.rdg_dcolor_from_acc(n, ptr(acc), ptr(state.geom["clamped"]), ptr(grads.dcolor), stream))
+        if grads.dcolor_mc:
+            # NVLS: the factors go straight into every rank's gathered buffer (multicast stores).  The kernel lasts as long as
+            # the NVLink transfer (its stores must be acknowledged), so it runs on a side stream beside the per-Gaussian backward
+            side = grads.dcolor_stream
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record()
+                side.wait_event(ev)
+                acc.record_stream(side)
+                state.geom["clamped"].record_stream(side)
+                check(lib.rdg_dcolor_multicast(n, ptr(acc), ptr(state.geom["clamped"]), grads.dcolor_mc, side.cuda_stream))
+            else:
+                check(lib.rdg_dcolor_multicast(n, ptr(acc), ptr(state.geom["clamped"]), grads.dcolor_mc, stream))
+        else:
+            check(lib.rdg_dcolor_from_acc(n, ptr(acc), ptr(state.geom["clamped"]), ptr(grads.dcolor), stream))
         after_blend()
     if stage_hook:
         stage_hook("blend_bwd")
@@ -428,7 +447,18 @@ def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: Sce
         if grads.g7_scratch is None:
             grads.g7_scratch = torch.empty(state.scene.motion_coeff.shape[0], 8, dtype=torch.float32, device=dev)
         g.g7_scratch = ptr(grads.g7_scratch)
-    check(lib.rdg_preprocess_bwd(C.byref(sc_s), C.byref(vw_s), C.byref(gm_s), ptr(acc), C.byref(g), stream))
+    ns, nd = state.scene.counts()
+    if after_model is not None and ns > 0 and nd > 0:
+        for models, tag in ((2, "dynamic"), (1, "static")):
+            g.models = models
+            check(lib.rdg_preprocess_bwd(C.byref(sc_s), C.byref(vw_s), C.byref(gm_s), ptr(acc), C.byref(g), stream))
+            after_model(tag)
+    else:
+        g.models = 0
+        check(lib.rdg_preprocess_bwd(C.byref(sc_s), C.byref(vw_s), C.byref(gm_s), ptr(acc), C.byref(g), stream))
+        if after_model is not None:
+            after_model("dynamic" if nd > 0 else "static")
+            after_model("static" if nd > 0 else "dynamic")
     if stage_hook:
         stage_hook("preprocess_bwd")
     return acc

@@ -299,16 +299,25 @@ class SplatTrainStep:
             if dcolor_slot is not None:
                 gst.sh_dc = gst.sh_rest = gdy.sh_dc = gdy.sh_rest = None
                 dcolor = self.dcolor_local[dcolor_slot]
-            grads = SceneGrads(st=gst, dy=gdy, means2D=self.means2D_grad, dcolor=dcolor,
+            dcolor_mc = 0
+            if dcolor_slot is not None and self._mc_base:
+                n_all = self.ns + self.nd
+                block = (self._parity * self.views_per_rank * self.world_size + self._rank * self.views_per_rank + dcolor_slot)
+                dcolor_mc = self._mc_base + 4 * block * n_all * 3
+            grads = SceneGrads(st=gst, dy=gdy, means2D=self.means2D_grad, dcolor=dcolor, dcolor_mc=dcolor_mc,
+                               dcolor_stream=self.comm_stream if dcolor_mc else None,
                                viewmatrix=self.view_grad,
                                motion_coeff=self.g("motion_coeff").view(self.nd, self.num_basis) if deform else None,
                                table=self.g("table") if deform else None, basis_t=self.g("basis_t") if deform else None,
                                g7_scratch=self._g7)
-            hook = None
+            hook = model_hook = None
             if dcolor_slot is not None and dcolor_slot == self.views_per_rank - 1:
                 hook = self._start_gather      # the factors of every local view are final: gather them now
+                if self.views_per_rank == 1 and self.world_size > 1 and self._bucketed:
+                    model_hook = self._after_model   # one view per rank: each model's range is final after its own launch
             engine.render_backward(state, self.dL_dcolor, self.dL_ddepth if use_depth else None,
-                                   self.dL_dalpha if use_alpha else None, grads, stage_hook=self._mark, after_blend=hook)
+                                   self.dL_dalpha if use_alpha else None, grads, stage_hook=self._mark, after_blend=hook,
+                                   after_model=model_hook)
         finally:
             self.grads = saved
         if accumulate:
@@ -322,7 +331,7 @@ class SplatTrainStep:
 
     # -- data-parallel exchange with factored SH gradients -----------------------------------------
     def enable_factored_exchange(self, views_per_rank: int, world_size: int, copy_engine_gather: bool = True,
-                                 gather_streams: int = 4):
+                                 gather_streams: int = 4, bucketed: bool = True, sm_reserve: int = 16, multicast: bool = False):
         """Buffers and the side streams for exchange_grads(): the local factors [views_per_rank, N, 3], the gathered
         ones, and a communication stream on which the collectives overlap the backward kernels.
 
@@ -330,29 +339,43 @@ class SplatTrainStep:
         let every rank push its own block into all peers' buffers with plain device-to-device copies - NVLink
         through the copy engines, no SMs, so the gather really runs under the per-Gaussian backward (whose
         persistent CTAs own the whole register file; an NCCL kernel only gets in once they retire).  Falls back to
-        NCCL's all-gather when symmetric memory cannot be set up."""
+        NCCL's all-gather when symmetric memory cannot be set up.
+
+        multicast: write the factors through the NVLink-switch multicast mapping of the gathered buffer from the kernel that
+        computes them (rdg_dcolor_multicast, multimem.st) instead of pushing them with the copy engines.  Measured on 8 B200s
+        (profiles/r02_timeline_n8_mc.txt): the kernel lasts 0.44 ms - every rank receives 7 x 24 MB and its stores must be
+        acknowledged - and holds SMs the per-Gaussian backward needs (0.19 -> 0.43 ms), against 0.33 ms of copy-engine pushes
+        that cost no SM time; off by default."""
         import torch.distributed as dist
         n = self.ns + self.nd
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.views_per_rank, self.world_size = int(views_per_rank), int(world_size)
         if self.views_per_rank * self.world_size > 16:
             raise ValueError("factored exchange: rdg_sh_grad_views stages at most 16 views per step (views_per_rank * world_size)")
-        self._fx_args = (views_per_rank, world_size, copy_engine_gather, gather_streams)
+        self._fx_args = (views_per_rank, world_size, copy_engine_gather, gather_streams, bucketed, sm_reserve, multicast)
+        self._symm = None
+        self._mc_base = 0
         v_total = self.views_per_rank * self.world_size
         self._symm = None
         self.dcolor_all = None
         if copy_engine_gather and self.world_size > 1 and dist.is_initialized():
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                buf = symm_mem.empty(v_total, n, 3, dtype=torch.float32, device=self.dev)
+                # two gathered buffers used alternately: step k + 1 writes the other one, so no rank can overwrite factors a slower
+                # peer is still reading (the all-reduce of step k + 1 cannot complete before every rank has finished step k)
+                buf = symm_mem.empty(2, v_total, n, 3, dtype=torch.float32, device=self.dev)
                 group = self.pg if self.pg is not None else dist.group.WORLD
                 self._symm = symm_mem.rendezvous(buf, group)
-                self.dcolor_all = buf
+                self._dc_all2 = buf
+                self.dcolor_all = buf[0]
                 self._rank = dist.get_rank(group)
                 k = self.views_per_rank
-                # my block inside every peer's gathered buffer
-                self._peer_blocks = [self._symm.get_buffer(r, buf.shape, torch.float32)[self._rank * k:(self._rank + 1) * k]
-                                     for r in range(self.world_size)]
+                # NVLS: the multicast mapping of the buffer - a store to it lands in every rank's copy (rdg_dcolor_multicast)
+                mc = int(getattr(self._symm, "multicast_ptr", 0) or 0)
+                self._mc_base = mc if (multicast and mc) else 0
+                # my block inside every peer's gathered buffer (copy-engine path, when there is no multicast mapping)
+                self._peer_blocks = [[self._symm.get_buffer(r, buf.shape, torch.float32)[par, self._rank * k:(self._rank + 1) * k]
+                                      for r in range(self.world_size)] for par in range(2)]
                 self._gather_streams = [torch.cuda.Stream(device=self.dev) for _ in range(max(1, int(gather_streams)))]
                 self._ev_push = [torch.cuda.Event() for _ in self._gather_streams]
             except Exception as e:   # noqa: BLE001 - any failure here only costs the overlap, never correctness
@@ -360,24 +383,43 @@ class SplatTrainStep:
                 self._symm = None
                 self.dcolor_all = None
         if self.dcolor_all is None:
-            self.dcolor_all = torch.zeros(v_total, n, 3, **f32)
-        self.dcolor_all.zero_()
+            self._dc_all2 = torch.zeros(2, v_total, n, 3, **f32)
+            self.dcolor_all = self._dc_all2[0]
+            self._mc_base = 0
+        self._dc_all2.zero_()
+        self._parity = 0
         self.dcolor_local = torch.zeros(self.views_per_rank, n, 3, **f32)
         self.comm_stream = torch.cuda.Stream(device=self.dev)
+        self.ar_stream = torch.cuda.Stream(device=self.dev)     # the all-reduces do not queue behind the gather
         self._ev_factors, self._ev_gathered = torch.cuda.Event(), torch.cuda.Event()
         self._ev_backward, self._ev_reduced = torch.cuda.Event(), torch.cuda.Event()
         self._ev_barrier = torch.cuda.Event()
         self._gather_started = False
+        # bucketed all-reduce of the non-SH range: the per-Gaussian backward runs one launch per model (dynamic first) and each
+        # model's range is all-reduced on the communication stream as soon as it is written - the dynamic range (xyz .. opacity,
+        # motion coefficients, table) under the static model's kernel.  The persistent backward kernels leave `sm_reserve` SMs
+        # to NCCL (their CTAs take the whole register file of an SM; without free SMs the collective only starts when they retire).
+        self._bucketed = bool(bucketed) and self.world_size > 1 and self.ns > 0 and self.nd > 0
+        self._buckets = {"static": (self.layout["static.xyz"][0], self.layout["dynamic.xyz"][0]),
+                         "dynamic": (self.layout["dynamic.xyz"][0], sh_start(self.layout))}
+        self._ev_model = {t: torch.cuda.Event() for t in self._buckets}
+        self._ev_bucket = {t: torch.cuda.Event() for t in self._buckets}
+        self._buckets_started = 0
+        if self._bucketed:
+            _lib.set_tunable("sm_reserve", int(sm_reserve))
 
     def _start_gather(self):
         """All-gather of the factors on the communication stream (called right after the blend backward)."""
         self._ev_factors.record()
         with torch.cuda.stream(self.comm_stream):
-            self.comm_stream.wait_event(self._ev_factors)
-            if self._symm is not None:
-                # every rank is done reading the previous step's gathered factors (its rebuild kernel precedes
-                # _ev_factors on its compute stream), then the pushes go out on a few streams at once
+            if not self._mc_base:
+                self.comm_stream.wait_event(self._ev_factors)
+            if self._mc_base:
+                # the factors were multicast into every rank's buffer by the kernel that computed them: all that is left is the
+                # cross-rank barrier that says "everybody's stores have landed"
                 self._symm.barrier()
+            elif self._symm is not None:
+                # pushes through the copy engines on a few streams at once
                 self._ev_barrier.record(self.comm_stream)
                 ns = len(self._gather_streams)
                 for i, st in enumerate(self._gather_streams):
@@ -385,15 +427,26 @@ class SplatTrainStep:
                     with torch.cuda.stream(st):
                         for s in range(i, self.world_size, ns):
                             r = (self._rank + s) % self.world_size
-                            self._peer_blocks[r].copy_(self.dcolor_local, non_blocking=True)
+                            self._peer_blocks[self._parity][r].copy_(self.dcolor_local, non_blocking=True)
                         self._ev_push[i].record(st)
                 for ev in self._ev_push:
                     self.comm_stream.wait_event(ev)
                 self._symm.barrier()                    # every rank's pushes have landed everywhere
             else:
-                allgather_rows(self.dcolor_local, self.dcolor_all, self.pg)
+                allgather_rows(self.dcolor_local, self._dc_all2[self._parity], self.pg)
             self._ev_gathered.record(self.comm_stream)
         self._gather_started = True
+
+    def _after_model(self, tag: str):
+        """Called by engine.render_backward right after the per-Gaussian backward of model `tag`: all-reduce (mean over the
+        ranks) of that model's gradient range on the communication stream."""
+        lo, hi = self._buckets[tag]
+        self._ev_model[tag].record()
+        with torch.cuda.stream(self.ar_stream):
+            self.ar_stream.wait_event(self._ev_model[tag])
+            allreduce_flat(self.grads[lo:hi], 1.0 / self.world_size, self.pg)
+            self._ev_bucket[tag].record(self.ar_stream)
+        self._buckets_started += 1
 
     def exchange_grads(self, viewmats_all: torch.Tensor, basis_all: torch.Tensor):
         """Finish a data-parallel step whose local views ran with dcolor_slot=0..views_per_rank-1:
@@ -412,13 +465,20 @@ class SplatTrainStep:
         if not self._gather_started:
             self._start_gather()
         self._gather_started = False
-        self._ev_backward.record()
-        with torch.cuda.stream(self.comm_stream):
-            self.comm_stream.wait_event(self._ev_backward)
-            allreduce_flat(self.grads[:n_plain], 1.0 / self.world_size, self.pg)
-            if self.views_per_rank > 1:
-                self.grads[:n_plain].mul_(1.0 / self.views_per_rank)
-            self._ev_reduced.record(self.comm_stream)
+        if self._buckets_started == 2:
+            # both model ranges are already in flight (or done) on the communication stream
+            self._buckets_started = 0
+            with torch.cuda.stream(self.ar_stream):
+                self._ev_reduced.record(self.ar_stream)
+        else:
+            self._buckets_started = 0
+            self._ev_backward.record()
+            with torch.cuda.stream(self.ar_stream):
+                self.ar_stream.wait_event(self._ev_backward)
+                allreduce_flat(self.grads[:n_plain], 1.0 / self.world_size, self.pg)
+                if self.views_per_rank > 1:
+                    self.grads[:n_plain].mul_(1.0 / self.views_per_rank)
+                self._ev_reduced.record(self.ar_stream)
         cur.wait_event(self._ev_gathered)
         deform = self.nd > 0
         scene = SceneArgs(st=self._set("static"), dy=self._set("dynamic"), raw=True, use_deform=deform,
@@ -429,7 +489,8 @@ class SplatTrainStep:
         sc_s = engine._scene_struct(scene)
         gst, gdy = engine._setgrad_struct(self._setgrad("static")), engine._setgrad_struct(self._setgrad("dynamic"))
         check(lib.rdg_sh_grad_views(C.byref(sc_s), self.sh_degree, v_total, ptr(viewmats_all), ptr(basis_all),
-                                    ptr(self.dcolor_all), 1.0 / v_total, C.byref(gst), C.byref(gdy), _lib.stream_ptr()))
+                                    ptr(self._dc_all2[self._parity]), 1.0 / v_total, C.byref(gst), C.byref(gdy), _lib.stream_ptr()))
+        self._parity ^= 1
         cur.wait_event(self._ev_reduced)
         self._mark("exchange")
 
