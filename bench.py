@@ -315,12 +315,17 @@ def run_ours(args, rank, world, local_rank):
     all_vm, all_bt = [], []
     if factored:
         step.enable_factored_exchange(views_per_rank=1, world_size=world, copy_engine_gather=not args.nccl_gather,
-                                      bucketed=not args.no_bucketed, sm_reserve=args.sm_reserve, multicast=args.multicast)
+                                      bucketed=not args.no_bucketed, sm_reserve=args.sm_reserve, multicast=args.multicast,
+                                      sm_partition=not args.no_sm_partition, allreduce=args.allreduce, allreduce_ctas=args.allreduce_ctas)
         for j in range(len(my_views)):
             cs = [synthetic.make_camera(r + j * world, n_views, H, W, T) for r in range(world)]
             all_vm.append(torch.stack([c.world_view_transform.t().contiguous() for c in cs]).to(dev).contiguous())
             all_bt.append(torch.stack([step.p("table")[c.time_index] for c in cs]).contiguous())
 
+    # N > 1: dL/dSH stays in its factored form and is consumed by the SH groups' Adam update (rdg_sh_adam_views); the timed step
+    # ends when every rank holds the gathered factors and the all-reduced remaining range, i.e. everything its optimiser needs
+    defer_sh = factored and not args.materialize_sh
+    with_opt = [False]
     adam_state = None
     if args.adam:
         adam_state = (torch.zeros_like(step.params), torch.zeros_like(step.params))
@@ -362,7 +367,11 @@ def run_ours(args, rank, world, local_rank):
                 step.allreduce_grads(1.0 / world)
             else:
                 j = k % len(dev_inputs)
-                step.exchange_grads(all_vm[j], all_bt[j])
+                step.exchange_grads(all_vm[j], all_bt[j], defer_sh=defer_sh)
+        if with_opt[0]:
+            it_count[0] += 1
+            step.optimizer_step("static", it_count[0])
+            step.optimizer_step("dynamic", it_count[0])
         if adam_state is not None:
             it_count[0] += 1
             _lib.check(lib.rdg_adam(step.params.data_ptr(), step.grads.data_ptr(), adam_state[0].data_ptr(),
@@ -473,6 +482,28 @@ def run_ours(args, rank, world, local_rank):
         step.p("table").copy_(keep_table)
         step.p("basis_t").copy_(keep_bt)
 
+    # ---- the step INCLUDING the optimiser (GaussianAdam with the reference's groups, both models): not the metric, but it shows
+    # what the factored dL/dSH costs / saves end to end (N > 1: the SH groups step straight from the gathered factors) ----
+    opt_info = None
+    if not args.forward_only and not args.adam:
+        from rodygs_b200.optim import GaussianLRs
+        keep = step.params.clone()
+        step.attach_optimizer("static", GaussianLRs())
+        step.attach_optimizer("dynamic", GaussianLRs(scaling_lr=0.001, motion_coeff_lr=1.6e-4))
+        with_opt[0] = True
+        n_opt = max(5, min(args.steps, 30))
+        for k in range(3):
+            one_step(k)
+        ms_opt, per_step_opt, _, _ = timed(n_opt)
+        with_opt[0] = False
+        step.params.copy_(keep)
+        del keep
+        opt_info = {"ms_per_step": ms_opt / n_opt, "value": world * 1000.0 * n_opt / ms_opt, "unit": UNIT, "steps": n_opt,
+                    "ms_per_step_stats": pct(per_step_opt),
+                    "note": "fwd + loss + bwd" + (" + exchange" if world > 1 else "") + " + Adam over every parameter group of both models ("
+                            + ("f_dc / f_rest from the gathered dL/dSH factors by rdg_sh_adam_views, the rest by rdg_adam_groups" if defer_sh
+                               else "rdg_adam_groups") + "); not the headline metric"}
+
     # ---- per-stage device times from the events recorded inside the timed region ----
     stage_ms = {}
     prev = None
@@ -539,6 +570,13 @@ def run_ours(args, rank, world, local_rank):
             cpu = {"value": scaled, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                    "sample": desc + f"; scaled by algorithmic bytes ({sample_bytes / total_bytes:.3e}) to this workload",
                    "sample_value": rate}
+        if factored:
+            parallelism = (f"dp{world} (view-sharded; all-gather of the 12 B/Gaussian factors of dL/dSH + allreduce of the other gradients"
+                           + ("" if args.no_bucketed else f" per model under the other model's backward kernel, {args.sm_reserve} SMs left to NCCL")
+                           + (", dL/dSH kept factored for the SH groups' fused Adam (rdg_sh_adam_views) - not materialised in the timed step)"
+                              if defer_sh else ", dL/dSH rebuilt per rank)"))
+        else:
+            parallelism = f"dp{world} (view-sharded, allreduce of the flat gradient buffer)"
         line = {
             "metric": metric_name(args.config, args.forward_only),
             "value": value, "unit": UNIT if not args.forward_only else "frames/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
@@ -550,10 +588,7 @@ def run_ours(args, rank, world, local_rank):
                                 + (" + 0.01 mean(1 - alpha)" if w_alpha else "")) if not args.forward_only else "none (forward only)",
                        "pixels": P, "views_per_step": world, "l2": "inputs larger than L2 (params+SH 472 MB, sort buffers)",
                        "optimizer": "fused Adam in the timed region" if args.adam else "excluded (metric = raster fwd+bwd+loss)",
-                       "sync_free": True, "parallelism": (f"dp{world} (view-sharded; all-gather of the 12 B/Gaussian factors of dL/dSH + allreduce of "
-                                       "the other gradients" + ("" if args.no_bucketed else f" per model under the other model's backward kernel, {args.sm_reserve} SMs left to NCCL") +
-                                       ", dL/dSH rebuilt per rank)" if factored else
-                                       f"dp{world} (view-sharded, allreduce of the flat gradient buffer)")},
+                       "sync_free": True, "parallelism": parallelism},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps, "ms_per_step_stats": pct(per_step_e2e),
@@ -569,6 +604,7 @@ def run_ours(args, rank, world, local_rank):
                               "note": "whole step (all kernels + launch gaps) against the HBM peak"},
             "stage_ms": stage_ms,
             "basis_mlp": mlp_info,
+            "with_optimizer": opt_info,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -659,6 +695,13 @@ def main():
     ap.add_argument("--sm-reserve", type=int, default=16,
                     help="N>1: SMs the persistent backward kernels leave to NCCL while the bucketed all-reduce runs beside them")
     ap.add_argument("--timeline", default="", help="write the kernel timeline of one step (rank 0, torch.profiler) to this file")
+    ap.add_argument("--no-sm-partition", action="store_true",
+                    help="N>1: size the persistent backward grids for 148 - sm_reserve SMs instead of the SM-partitioned chunk queue (A/B)")
+    ap.add_argument("--allreduce", default="nccl", choices=["nccl", "multimem", "symm_op"],
+                    help="N>1: all-reduce of the non-SH gradient range: NCCL, the in-switch kernel rdg_allreduce_multimem, or torch's symm_mem op")
+    ap.add_argument("--allreduce-ctas", type=int, default=32)
+    ap.add_argument("--materialize-sh", action="store_true",
+                    help="N>1: rebuild dL/dSH of all views in the timed step (rdg_sh_grad_views) instead of leaving the factors to the fused SH Adam")
     ap.add_argument("--plain-allreduce", action="store_true",
                     help="N>1: all-reduce the whole flat gradient buffer instead of the factored SH exchange (A/B)")
     args = ap.parse_args()

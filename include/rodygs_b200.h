@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RDG_ABI_VERSION 7
+#define RDG_ABI_VERSION 8
 #define RDG_TILE 16
 #define RDG_NUM_BASIS_MAX 16
 
@@ -158,6 +158,9 @@ typedef struct RdgSceneGrad {
     int32_t models;          /* 0 or 3: both models; 1: the static model only; 2: the dynamic model only (+ dL/dtable, dL/dB(t)).
                               * The data-parallel step calls rdg_preprocess_bwd once per model so that the all-reduce of the
                               * first model's gradient range runs under the second model's kernel (viewmatrix accumulates). */
+    uint32_t* sm_queue;      /* optional device scratch, 4 uint32: with the "sm_reserve" tunable > 0 the persistent kernel then runs
+                              * SM-partitioned - CTAs that land on the reserved SMs exit, the others draw chunks from this counter -
+                              * so that a collective on another stream finds free SMs while it runs */
     float* dcolor;           /* optional [N,3]: dL/d(rgb) of every Gaussian after the SH clamp mask (zeros when it is not
                               * visible) - the 12-byte factors from which rdg_sh_grad_views rebuilds dL/dSH of all views
                               * of a data-parallel step; pass st/dy.sh_dc = sh_rest = NULL with it to skip the dSH rows */
@@ -176,6 +179,7 @@ uint64_t rdg_launch_count(void);
  *                  to a collective (NCCL) that runs beside them on another stream (their CTAs take the whole register file)
  *   "deterministic" 1: rdg_preprocess_bwd runs its kernels with one CTA so that the cross-CTA float atomics of dL/dV,
  *                  dL/dtable and dL/dB(t) land in a fixed order (test mode, slow; pair it with rdg_blend_bwd_deterministic)
+ *   "ar_unroll"    2 / 4 (default) / 8: 16-byte vectors each thread of rdg_allreduce_multimem keeps in flight
  * Returns RDG_E_ARG for an unknown name. */
 int rdg_set_tunable(const char* name, int32_t value);
 
@@ -231,12 +235,7 @@ int rdg_blend_bwd_deterministic(int64_t n, const RdgGeom* geom, const RdgBins* b
 int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, const RdgGeom* geom,
                        const float* acc, const RdgSceneGrad* grads, void* stream);
 
-/* dL/dSH of all views of a data-parallel step from its rank-1 factors (SURVEY.md §8e): for every Gaussian
- *   dL/dSH[k][c] = scale * sum_v Y_k(normalize(x(t_v) - campos_v)) * dcolor[v][c],
- * with x(t_v) the (deformed, scene.raw) mean at view v's time.  viewmatrices [V,16] glm storage, basis_ts [V,K,7]
- * (B(t_v), needed when scene.use_deform), dcolor [V,N,3] as written by rdg_preprocess_bwd through
- * RdgSceneGrad.dcolor (gathered from all ranks).  Overwrites grad_*->sh_dc / sh_rest; V <= 16. */
-/* The same factors straight from the blend backward's accumulators (acc rows 6..8, clamp mask applied), so that
+/* The 12-byte factors of dL/dSH straight from the blend backward's accumulators (acc rows 6..8, clamp mask applied), so that
  * their all-gather can start before rdg_preprocess_bwd runs.  dcolor [N,3]. */
 int rdg_dcolor_from_acc(int64_t n, const float* acc, const uint8_t* clamped, float* dcolor, void* stream);
 /* ... and written through an NVLink-switch MULTICAST mapping of this rank's block of the gathered buffer (symmetric memory:
@@ -245,9 +244,42 @@ int rdg_dcolor_from_acc(int64_t n, const float* acc, const uint8_t* clamped, flo
  * before the gathered buffer is read.  Needs NVSwitch multicast support (NVLS); use rdg_dcolor_from_acc + copies otherwise. */
 int rdg_dcolor_multicast(int64_t n, const float* acc, const uint8_t* clamped, float* dcolor_mc, void* stream);
 
+/* dL/dSH of all views of a data-parallel step from its rank-1 factors (SURVEY.md §8e): for every Gaussian
+ *   dL/dSH[k][c] = scale * sum_v Y_k(normalize(x(t_v) - campos_v)) * dcolor[v][c],
+ * with x(t_v) the (deformed, scene.raw) mean at view v's time.  viewmatrices [V,16] glm storage, basis_ts [V,K,7]
+ * (B(t_v), needed when scene.use_deform), dcolor [V,N,3] as written by rdg_preprocess_bwd through
+ * RdgSceneGrad.dcolor (gathered from all ranks).  Overwrites grad_*->sh_dc / sh_rest; V <= 16.  sm_queue: NULL, or 4 uint32 of
+ * device scratch for the SM-partitioned mode (RdgSceneGrad.sm_queue). */
 int rdg_sh_grad_views(const RdgScene* scene, int32_t sh_degree, int32_t n_views, const float* viewmatrices,
                       const float* basis_ts, const float* dcolor, float scale, const RdgSetGrad* grad_static,
-                      const RdgSetGrad* grad_dynamic, void* stream);
+                      const RdgSetGrad* grad_dynamic, uint32_t* sm_queue, void* stream);
+
+/* The same sum over views fused into its consumer: torch.optim.Adam (eps as given, no weight decay) over the f_dc / f_rest
+ * groups (src/trainer/rodygs_static.py:118-123) of one or both models, the gradient of each 256-Gaussian chunk rebuilt in
+ * shared memory from the gathered factors - dL/dSH (81 % of the gradient buffer) is never written to HBM.  Updates
+ * scene->st / dy.sh_dc [n,3] and sh_rest [n,45] IN PLACE (contiguous, 16-byte aligned) and the four moment tensors of
+ * RdgShAdam.  `scale` multiplies the gradient (1 / views, times any loss scale).  Run it BEFORE the Adam step that moves the
+ * means / motion coefficients the directions are evaluated from. */
+typedef struct RdgShAdam {
+    float* exp_avg_dc;      /* [n,3]  */
+    float* exp_avg_sq_dc;   /* [n,3]  */
+    float* exp_avg_rest;    /* [n,45] */
+    float* exp_avg_sq_rest; /* [n,45] */
+    float lr_dc;            /* feature_lr */
+    float lr_rest;          /* feature_lr / 20 */
+    int32_t step;           /* this optimiser's step count, >= 1 (bias correction); 0: leave this model alone */
+    int32_t reserved;
+} RdgShAdam;
+int rdg_sh_adam_views(const RdgScene* scene, int32_t sh_degree, int32_t n_views, const float* viewmatrices,
+                      const float* basis_ts, const float* dcolor, float scale, const RdgShAdam* adam_static,
+                      const RdgShAdam* adam_dynamic, float beta1, float beta2, float eps, void* stream);
+
+/* In-switch all-reduce (sum * scale) of a float range that every rank holds at the same offset of a symmetric-memory buffer:
+ * mc_range = the NVLink-switch multicast address of the range (16-byte aligned, n_floats % 4 == 0).  Rank `rank` of `world`
+ * reduces its 1 / world slice with multimem.ld_reduce and broadcasts it with multimem.st; `ctas` x 512 threads (0: 32 CTAs).
+ * The caller puts a cross-rank barrier on the stream before (all ranks' values written) and after (all slices landed).  Needs
+ * NVSwitch multicast (NVLS); the fallback is the NCCL all-reduce of the same range. */
+int rdg_allreduce_multimem(float* mc_range, int64_t n_floats, int32_t rank, int32_t world, float scale, int32_t ctas, void* stream);
 
 /* ---- losses ----------------------------------------------------------------- */
 

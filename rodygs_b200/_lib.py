@@ -59,11 +59,16 @@ class RdgSetGrad(C.Structure):
 class RdgSceneGrad(C.Structure):
     _fields_ = [("st", RdgSetGrad), ("dy", RdgSetGrad), ("colors_precomp", c_ptr), ("means2D", c_ptr),
                 ("viewmatrix", c_ptr), ("motion_coeff", c_ptr), ("table", c_ptr), ("basis_t", c_ptr), ("g7_scratch", c_ptr),
-                ("models", C.c_int32), ("dcolor", c_ptr)]
+                ("models", C.c_int32), ("sm_queue", c_ptr), ("dcolor", c_ptr)]
 
 
 class RdgDensifyField(C.Structure):
     _fields_ = [("src", c_ptr), ("dst", c_ptr), ("width", C.c_int32), ("mode", C.c_int32)]
+
+
+class RdgShAdam(C.Structure):
+    _fields_ = [("exp_avg_dc", c_ptr), ("exp_avg_sq_dc", c_ptr), ("exp_avg_rest", c_ptr), ("exp_avg_sq_rest", c_ptr),
+                ("lr_dc", C.c_float), ("lr_rest", C.c_float), ("step", C.c_int32), ("reserved", C.c_int32)]
 
 
 class RdgAdamGroup(C.Structure):
@@ -116,7 +121,10 @@ SYMBOLS = {
     "rdg_dcolor_from_acc": (C.c_int, [C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "rdg_dcolor_multicast": (C.c_int, [C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "rdg_sh_grad_views": (C.c_int, [C.POINTER(RdgScene), C.c_int32, C.c_int32, c_ptr, c_ptr, c_ptr, C.c_float,
-                                    C.POINTER(RdgSetGrad), C.POINTER(RdgSetGrad), c_ptr]),
+                                    C.POINTER(RdgSetGrad), C.POINTER(RdgSetGrad), c_ptr, c_ptr]),
+    "rdg_sh_adam_views": (C.c_int, [C.POINTER(RdgScene), C.c_int32, C.c_int32, c_ptr, c_ptr, c_ptr, C.c_float,
+                                    C.POINTER(RdgShAdam), C.POINTER(RdgShAdam), C.c_float, C.c_float, C.c_float, c_ptr]),
+    "rdg_allreduce_multimem": (C.c_int, [c_ptr, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_int32, c_ptr]),
     "rdg_l1_dssim_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "rdg_l1_dssim": (C.c_int, [c_ptr, c_ptr, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, c_ptr, c_ptr,
                                c_ptr, C.c_int64, c_ptr]),
@@ -172,7 +180,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.rdg_abi_version() != 7:
+    if lib.rdg_abi_version() != 8:
         raise RuntimeError("librodygs_b200.so ABI version mismatch")
     _lib = lib
     return lib

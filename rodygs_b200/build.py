@@ -33,6 +33,7 @@ SOURCES = {
     "blend_r1.cu": [],
     "preprocess_bwd.cu": [],
     "sh_grad_views.cu": [],
+    "exchange.cu": [],
     "loss.cu": [],
     "densify.cu": [],
     "optim.cu": [],

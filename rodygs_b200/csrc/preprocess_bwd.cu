@@ -30,6 +30,8 @@ struct PreBwdParams {
     int diff_smem;     // B(t) - table rows staged in shared memory (rdg_stage_diff)
     int dtab_atomic;   // no CSR: accumulate dL/dtable with global atomics from this kernel
     int64_t c_begin, c_end;   // chunk range of this launch (RdgSceneGrad.models: one model at a time under data parallelism)
+    uint32_t* sm_queue;       // non-NULL: SM-partitioned mode - CTAs that land on an SM >= sm_limit exit at once, the others take
+    int sm_limit;             // chunks from this counter, so that SMs sm_limit.. stay FREE for a collective on another stream
 };
 
 template <int DEG>
@@ -67,12 +69,18 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
     constexpr int K = (DEG + 1) * (DEG + 1);
     constexpr int NREST = 3 * (K - 1);
     const RdgScene& sc = p.sc;
+    if (p.sm_queue) {                         // leave the upper SMs to NCCL (a persistent grid cannot be pinned, but it can decline)
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        if ((int)smid >= p.sm_limit) return;
+    }
     const bool use_sh = sc.colors_precomp == nullptr;
     const bool deform = RAW && sc.use_deform && sc.n_dynamic > 0;
     float* sh_s = smem;                       // [256][SH_ROW] in: SH rest coefficients, out: their gradients
     float* bt_s = smem + RDG_BLOCK * SH_ROW;  // [16*7] B(t)
     __shared__ float red_s[RDG_BLOCK / 32][16];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ long long q_s[2];
 
     RdgCam cam;
     rdg_load_cam(cam, p.view.viewmatrix, p.view.projmatrix, p.view.tanfovx, p.view.tanfovy, p.view.width, p.view.height);
@@ -86,8 +94,17 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
         for (int e = threadIdx.x; e < sc.num_basis * 7; e += RDG_BLOCK) bt_s[e] = sc.basis_t[e];
         if (diff_s) rdg_stage_diff(sc, sc.basis_t, diff_s, RDG_BLOCK);
     }
-    if (threadIdx.x == 0) rdg_mbar_init(&bar, 1);
+    if (threadIdx.x == 0) {
+        rdg_mbar_init(&bar, 1);
+        if (p.sm_queue) {                     // this CTA's first two chunks
+            q_s[0] = p.c_begin + (long long)atomicAdd(p.sm_queue, 1u);
+            q_s[1] = p.c_begin + (long long)atomicAdd(p.sm_queue, 1u);
+        }
+    }
     __syncthreads();
+    const bool queued = p.sm_queue != nullptr;
+    long long chunk_nx = queued ? q_s[1] : p.c_begin + (long long)blockIdx.x + gridDim.x;
+    const long long chunk_first = queued ? q_s[0] : p.c_begin + (long long)blockIdx.x;
 
     float poseV[12];   // dL/dV rows 0..2 (row-major), this thread's partial sum
     float dcam[3] = {0.f, 0.f, 0.f};
@@ -109,11 +126,12 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
     };
     int radius_pf = 0;
     unsigned clamped_pf = 0;
-    if (p.c_begin + (int64_t)blockIdx.x < p.c_end) {
+    if (chunk_first < p.c_end) {
         int64_t gi;
-        if (chunk_slot(p.c_begin + blockIdx.x, gi)) { radius_pf = p.geom.radii[gi]; clamped_pf = p.geom.clamped[gi]; }
+        if (chunk_slot(chunk_first, gi)) { radius_pf = p.geom.radii[gi]; clamped_pf = p.geom.clamped[gi]; }
     }
-    for (int64_t chunk = p.c_begin + blockIdx.x; chunk < p.c_end; chunk += gridDim.x) {
+    int q_par = 0;
+    for (int64_t chunk = chunk_first; chunk < p.c_end; ) {
         const bool dyn = chunk >= cs;
         const RdgSet& set = dyn ? sc.dy : sc.st;
         const RdgSetGrad& gs = dyn ? p.gr.dy : p.gr.st;
@@ -128,10 +146,12 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
         const bool vis = radius > 0;
         radius_pf = 0;
         clamped_pf = 0;
-        if (chunk + gridDim.x < p.c_end) {
+        if (chunk_nx < p.c_end) {
             int64_t gi;
-            if (chunk_slot(chunk + gridDim.x, gi)) { radius_pf = p.geom.radii[gi]; clamped_pf = p.geom.clamped[gi]; }
+            if (chunk_slot(chunk_nx, gi)) { radius_pf = p.geom.radii[gi]; clamped_pf = p.geom.clamped[gi]; }
         }
+        // the chunk after the next one (claimed by thread 0, published by the barrier below, read at the end of the iteration)
+        if (queued && threadIdx.x == 0) q_s[q_par] = p.c_begin + (long long)atomicAdd(p.sm_queue, 1u);
 
         // ---- stage the SH rest rows ----
         const bool full_rows = use_sh && set.sh_rest_stride == SH_ROW;
@@ -139,6 +159,9 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
         const bool tma_out = full_rows && p.use_tma && gs.sh_rest != nullptr && (cnt & 3) == 0;
         if (threadIdx.x == 0 && store_pending) { rdg_bulk_store_wait_read(); store_pending = false; }
         __syncthreads();   // previous chunk fully written out / read
+        // (two slots: thread 0 may write the next iteration's claim while slower threads still read this one)
+        const long long chunk_after = queued ? q_s[q_par] : chunk_nx + (long long)gridDim.x;
+        q_par ^= 1;
         if (use_sh && NREST > 0) {
             if (tma_in) {
                 if (threadIdx.x == 0) {
@@ -414,6 +437,8 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
                 }
             }
         }
+        chunk = chunk_nx;
+        chunk_nx = chunk_after;
     }
     if (threadIdx.x == 0 && store_pending) rdg_bulk_store_wait_read();
 
@@ -631,6 +656,8 @@ extern "C" int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, co
     }
     const int64_t cs_h = (scene->n_static + RDG_BLOCK - 1) / RDG_BLOCK, cd_h = (scene->n_dynamic + RDG_BLOCK - 1) / RDG_BLOCK;
     const bool do_static = grads->models != 2, do_dynamic = grads->models != 1;
+    p.sm_queue = nullptr;
+    p.sm_limit = 0;
     p.c_begin = do_static ? 0 : cs_h;
     p.c_end = do_dynamic ? cs_h + cd_h : cs_h;
     const int64_t chunks = p.c_end - p.c_begin;
@@ -639,8 +666,15 @@ extern "C" int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, co
     int sms = RDG_SM_COUNT - rdg_tunable(RDG_TUN_SM_RESERVE);
     if (sms < 8) sms = 8;
     const int64_t cap = (int64_t)sms * 2;
-    const int grid = (int)(chunks < cap ? chunks : cap);
+    int grid = (int)(chunks < cap ? chunks : cap);
     cudaStream_t s = (cudaStream_t)stream;
+    if (grads->sm_queue && sms < RDG_SM_COUNT && chunks > cap && rdg_tunable(RDG_TUN_DETERMINISTIC) == 0) {
+        // SM-partitioned mode: a full-machine grid whose CTAs on SMs >= sms exit at once; the others share a chunk queue
+        RDG_CUDA(cudaMemsetAsync(grads->sm_queue, 0, 4 * sizeof(uint32_t), s));
+        p.sm_queue = grads->sm_queue;
+        p.sm_limit = sms;
+        grid = RDG_SM_COUNT * 2;
+    }
     const int rc = scene->raw ? launch_bwd_deg<true>(p, view->sh_degree, grid, smem, s)
                               : launch_bwd_deg<false>(p, view->sh_degree, grid, smem, s);
     if (rc) return rc;

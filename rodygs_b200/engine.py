@@ -372,6 +372,7 @@ class SceneGrads:
     basis_t: Optional[torch.Tensor] = None      # must be zero-initialised
     g7_scratch: Optional[torch.Tensor] = None   # [nd,8] scratch (allocated on demand)
     dcolor: Optional[torch.Tensor] = None       # [N,3] factors of dL/dSH for the data-parallel exchange
+    sm_queue: Optional[torch.Tensor] = None     # [4] int32 scratch: SM-partitioned per-Gaussian backward (data parallel)
     dcolor_mc: int = 0                          # multicast address of this view's block of the gathered factors (0: none)
     dcolor_stream: Optional[torch.cuda.Stream] = None   # side stream for the multicast kernel (its stores take NVLink time)
 
@@ -443,6 +444,7 @@ def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: Sce
     g.colors_precomp, g.means2D, g.viewmatrix = ptr(grads.colors_precomp), ptr(grads.means2D), ptr(grads.viewmatrix)
     g.motion_coeff, g.table, g.basis_t = ptr(grads.motion_coeff), ptr(grads.table), ptr(grads.basis_t)
     g.dcolor = None if early else ptr(grads.dcolor)
+    g.sm_queue = ptr(grads.sm_queue)
     if state.scene.use_deform and state.scene.frame_order is not None and grads.table is not None:
         if grads.g7_scratch is None:
             grads.g7_scratch = torch.empty(state.scene.motion_coeff.shape[0], 8, dtype=torch.float32, device=dev)

@@ -78,13 +78,14 @@ class GaussianAdam:
         off, n = self.ranges[name]
         return self.exp_avg[off:off + n], self.exp_avg_sq[off:off + n]
 
-    def step(self, params: torch.Tensor, grads: torch.Tensor, iteration: int, grad_scale: float = 1.0):
-        """update_learning_rate(iteration) + optimizer.step() (rodygs.py:209,364)."""
+    def step(self, params: torch.Tensor, grads: torch.Tensor, iteration: int, grad_scale: float = 1.0, skip=()):
+        """update_learning_rate(iteration) + optimizer.step() (rodygs.py:209,364).  skip: group names another kernel has
+        already stepped for this iteration (the SH groups, SplatTrainStep._sh_adam_from_factors)."""
         _lib.require_cuda(params, grads)
         if params.numel() != self.exp_avg.numel() or grads.numel() != params.numel():
             raise RuntimeError("optimizer state does not match the flat buffers (rebuild it after densification)")
         lr = self.lrs.group_lrs(iteration, self.spatial_lr_scale)
-        live = [(name, off, n) for name, (off, n) in self.ranges.items() if n > 0]
+        live = [(name, off, n) for name, (off, n) in self.ranges.items() if n > 0 and name not in skip]
         arr = (_lib.RdgAdamGroup * len(live))()
         for k, (name, off, n) in enumerate(live):
             arr[k].begin, arr[k].end, arr[k].lr = off, off + n, lr[name]

@@ -14,6 +14,7 @@ from __future__ import annotations
 import ctypes as C
 import copy
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -64,6 +65,11 @@ def shard_views(n_views: int, world_size: int, rank: int) -> List[int]:
     return [v for v in range(n_views) if v % world_size == rank]
 
 
+# ReduceOp.AVG saves the scaling pass, but NCCL has no NVLS (in-switch) reduction for it (pre-multiplied sum) and falls back
+# to a ring; RDG_AR_SUM=1 selects SUM + a scaling pass instead (A/B switch, see profiles/README.md)
+AVG_ON_COLLECTIVE = os.environ.get("RDG_AR_SUM", "0") != "1"
+
+
 def allreduce_flat(buf: torch.Tensor, scale: Optional[float] = None, group=None) -> torch.Tensor:
     """The data path's exchange step for a flat gradient range: in-place sum over the data-parallel group
     (NCCL on GPUs, gloo in the CPU tests), then an optional scale (1 / views for a mean over the step's
@@ -72,7 +78,7 @@ def allreduce_flat(buf: torch.Tensor, scale: Optional[float] = None, group=None)
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         world = dist.get_world_size(group)
-        if buf.is_cuda and scale is not None and abs(scale * world - 1.0) < 1e-12:
+        if buf.is_cuda and scale is not None and abs(scale * world - 1.0) < 1e-12 and AVG_ON_COLLECTIVE:
             dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=group)
             return buf
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
@@ -137,6 +143,7 @@ class SplatTrainStep:
         self._loss_ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.dev)
         self.views_per_rank = 1
         self.last_state: Optional[engine.FwdState] = None
+        self._deferred = None      # exchange_grads(defer_sh=True): the factors the next optimizer_step consumes
         self.stage_events = None   # set by enable_stage_timing()
 
     def _load_scene(self, scene: Dict):
@@ -163,6 +170,7 @@ class SplatTrainStep:
         if hasattr(self, "_grads_tmp"):
             del self._grads_tmp
         self.last_state = None
+        self._deferred = None      # factors of the old Gaussian set
 
     # -- views into the flat buffers --------------------------------------------------------
     def _slice(self, buf: torch.Tensor, name: str) -> torch.Tensor:
@@ -299,6 +307,8 @@ class SplatTrainStep:
             if dcolor_slot is not None:
                 gst.sh_dc = gst.sh_rest = gdy.sh_dc = gdy.sh_rest = None
                 dcolor = self.dcolor_local[dcolor_slot]
+            model_hook_wanted = (dcolor_slot is not None and dcolor_slot == self.views_per_rank - 1 and self.views_per_rank == 1
+                                 and getattr(self, "world_size", 1) > 1 and getattr(self, "_bucketed", False))
             dcolor_mc = 0
             if dcolor_slot is not None and self._mc_base:
                 n_all = self.ns + self.nd
@@ -306,6 +316,7 @@ class SplatTrainStep:
                 dcolor_mc = self._mc_base + 4 * block * n_all * 3
             grads = SceneGrads(st=gst, dy=gdy, means2D=self.means2D_grad, dcolor=dcolor, dcolor_mc=dcolor_mc,
                                dcolor_stream=self.comm_stream if dcolor_mc else None,
+                               sm_queue=self._sm_queue if (model_hook_wanted and self._sm_partition) else None,
                                viewmatrix=self.view_grad,
                                motion_coeff=self.g("motion_coeff").view(self.nd, self.num_basis) if deform else None,
                                table=self.g("table") if deform else None, basis_t=self.g("basis_t") if deform else None,
@@ -331,7 +342,8 @@ class SplatTrainStep:
 
     # -- data-parallel exchange with factored SH gradients -----------------------------------------
     def enable_factored_exchange(self, views_per_rank: int, world_size: int, copy_engine_gather: bool = True,
-                                 gather_streams: int = 4, bucketed: bool = True, sm_reserve: int = 16, multicast: bool = False):
+                                 gather_streams: int = 4, bucketed: bool = True, sm_reserve: int = 16, multicast: bool = False,
+                                 sm_partition: bool = True, allreduce: str = "nccl", allreduce_ctas: int = 32):
         """Buffers and the side streams for exchange_grads(): the local factors [views_per_rank, N, 3], the gathered
         ones, and a communication stream on which the collectives overlap the backward kernels.
 
@@ -352,7 +364,35 @@ class SplatTrainStep:
         self.views_per_rank, self.world_size = int(views_per_rank), int(world_size)
         if self.views_per_rank * self.world_size > 16:
             raise ValueError("factored exchange: rdg_sh_grad_views stages at most 16 views per step (views_per_rank * world_size)")
-        self._fx_args = (views_per_rank, world_size, copy_engine_gather, gather_streams, bucketed, sm_reserve, multicast)
+        self._fx_args = (views_per_rank, world_size, copy_engine_gather, gather_streams, bucketed, sm_reserve, multicast, sm_partition,
+                         allreduce, allreduce_ctas)
+        # sm_partition: the persistent per-Gaussian kernels launch a full-machine grid whose CTAs on the reserved SMs exit at once
+        # (chunk queue, RdgSceneGrad.sm_queue) instead of a smaller grid that the hardware may place on any SM
+        self._sm_partition = bool(sm_partition)
+        # allreduce: how the non-SH gradient range is summed over the ranks.
+        #   "nccl"      torch.distributed.all_reduce (ReduceOp.AVG: a ring; NCCL has no in-switch reduction for AVG)
+        #   "multimem"  the gradient buffer moves into symmetric memory and rdg_allreduce_multimem reduces it inside the NVLink
+        #               switch (multimem.ld_reduce + multimem.st, the 1 / world scale fused), bracketed by cross-rank barriers
+        #   "symm_op"   torch.ops.symm_mem.multimem_all_reduce_ on the same buffer + a scaling pass (library kernel, A/B)
+        import torch.distributed as dist
+        self._ar_mode, self._ar_ctas = "nccl", int(allreduce_ctas)
+        self._grads_symm = None
+        if allreduce != "nccl" and self.world_size > 1 and dist.is_initialized():
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                group = self.pg if self.pg is not None else dist.group.WORLD
+                buf = symm_mem.empty(self.grads.numel(), dtype=torch.float32, device=self.dev)
+                hdl = symm_mem.rendezvous(buf, group)
+                if not int(getattr(hdl, "multicast_ptr", 0) or 0):
+                    raise RuntimeError("no multicast mapping (NVLS) for the gradient buffer")
+                buf.copy_(self.grads)
+                self.grads = buf                      # same layout; the views are rebuilt lazily (keyed on data_ptr)
+                self._grads_symm, self._ar_mode = hdl, allreduce
+                self._ar_group_name = group.group_name
+                self._ar_rank = dist.get_rank(group)
+            except Exception as e:   # noqa: BLE001 - the fallback is the NCCL ring
+                print(f"rodygs_b200: in-switch all-reduce unavailable ({type(e).__name__}: {e}); using NCCL")
+                self._ar_mode = "nccl"
         self._symm = None
         self._mc_base = 0
         v_total = self.views_per_rank * self.world_size
@@ -405,6 +445,7 @@ class SplatTrainStep:
         self._ev_model = {t: torch.cuda.Event() for t in self._buckets}
         self._ev_bucket = {t: torch.cuda.Event() for t in self._buckets}
         self._buckets_started = 0
+        self._sm_queue = torch.zeros(8, dtype=torch.int32, device=self.dev)
         if self._bucketed:
             _lib.set_tunable("sm_reserve", int(sm_reserve))
 
@@ -444,17 +485,37 @@ class SplatTrainStep:
         self._ev_model[tag].record()
         with torch.cuda.stream(self.ar_stream):
             self.ar_stream.wait_event(self._ev_model[tag])
-            allreduce_flat(self.grads[lo:hi], 1.0 / self.world_size, self.pg)
+            self._allreduce_range(lo, hi)
             self._ev_bucket[tag].record(self.ar_stream)
         self._buckets_started += 1
 
-    def exchange_grads(self, viewmats_all: torch.Tensor, basis_all: torch.Tensor):
+    def _allreduce_range(self, lo: int, hi: int):
+        """Mean over the ranks of self.grads[lo:hi], on the current stream."""
+        if self._ar_mode == "multimem":
+            hdl = self._grads_symm
+            hdl.barrier(channel=0)                   # every rank has written its gradients of this range
+            check(_lib.load().rdg_allreduce_multimem(int(hdl.multicast_ptr) + 4 * lo, hi - lo, self._ar_rank, self.world_size,
+                                                     1.0 / self.world_size, self._ar_ctas, _lib.stream_ptr()))
+            hdl.barrier(channel=0)                   # every rank's slice has landed everywhere
+        elif self._ar_mode == "symm_op":
+            torch.ops.symm_mem.multimem_all_reduce_(self.grads[lo:hi], "sum", self._ar_group_name)
+            self.grads[lo:hi].mul_(1.0 / self.world_size)
+        else:
+            allreduce_flat(self.grads[lo:hi], 1.0 / self.world_size, self.pg)
+
+    def exchange_grads(self, viewmats_all: torch.Tensor, basis_all: torch.Tensor, defer_sh: bool = False):
         """Finish a data-parallel step whose local views ran with dcolor_slot=0..views_per_rank-1:
         all-gather the 12-byte factors of dL/dSH (81 % of the gradient message as 192-byte blocks; started right
         after the blend backward, so it overlaps the per-Gaussian backward), all-reduce everything else on the
         communication stream while this stream rebuilds dL/dSH of ALL views from the factors (rdg_sh_grad_views).
         viewmats_all [V,4,4] glm storage and basis_all [V,K,7] in rank-major view order (rank r holds views
-        r*views_per_rank ..); the result in self.grads is the mean over the V views."""
+        r*views_per_rank ..); the result in self.grads is the mean over the V views.
+
+        defer_sh=True: dL/dSH is NOT materialised.  The gathered factors stay where they are and the next
+        optimizer_step(tag) of each model consumes them inside the Adam update of its f_dc / f_rest groups
+        (rdg_sh_adam_views: the gradient of a 256-Gaussian chunk only ever exists in shared memory), so the 384 MB
+        write + re-read of the SH gradient blocks disappears from the step.  self.g("*.features_*") is then stale;
+        materialize_sh_grads() rebuilds it on demand (tests, logging)."""
         lib = _lib.load()
         v_total = self.views_per_rank * self.world_size
         self._check_input("viewmats_all", viewmats_all, (v_total, 4, 4))
@@ -475,24 +536,62 @@ class SplatTrainStep:
             self._ev_backward.record()
             with torch.cuda.stream(self.ar_stream):
                 self.ar_stream.wait_event(self._ev_backward)
-                allreduce_flat(self.grads[:n_plain], 1.0 / self.world_size, self.pg)
+                self._allreduce_range(0, n_plain)
                 if self.views_per_rank > 1:
                     self.grads[:n_plain].mul_(1.0 / self.views_per_rank)
                 self._ev_reduced.record(self.ar_stream)
         cur.wait_event(self._ev_gathered)
+        self._deferred = None
+        if defer_sh:
+            # the factors of this step live in _dc_all2[parity] until the step after next overwrites them
+            self._deferred = {"viewmats": viewmats_all, "basis": basis_all, "dcolor": self._dc_all2[self._parity],
+                              "views": v_total, "pending": {"static", "dynamic"}}
+        else:
+            self._sh_from_factors(viewmats_all, basis_all, self._dc_all2[self._parity], v_total,
+                                  partitioned=self._bucketed and self._sm_partition)
+        self._parity ^= 1
+        cur.wait_event(self._ev_reduced)
+        self._mark("exchange")
+
+    def _factor_scene(self, basis_all):
         deform = self.nd > 0
         scene = SceneArgs(st=self._set("static"), dy=self._set("dynamic"), raw=True, use_deform=deform,
                           motion_coeff=self.p("motion_coeff").view(self.nd, self.num_basis) if deform else None,
                           time_ind=self.time_ind if deform else None, basis_t=basis_all[0] if deform else None,
                           table=self.p("table") if deform else None, spatial_lr_scale=self.spatial_lr_scale,
                           frame_order=self.frame_order, frame_offsets=self.frame_offsets)
-        sc_s = engine._scene_struct(scene)
+        return engine._scene_struct(scene)
+
+    def _sh_from_factors(self, viewmats_all, basis_all, dcolor_all, v_total, partitioned=False):
+        sc_s = self._factor_scene(basis_all)
         gst, gdy = engine._setgrad_struct(self._setgrad("static")), engine._setgrad_struct(self._setgrad("dynamic"))
-        check(lib.rdg_sh_grad_views(C.byref(sc_s), self.sh_degree, v_total, ptr(viewmats_all), ptr(basis_all),
-                                    ptr(self._dc_all2[self._parity]), 1.0 / v_total, C.byref(gst), C.byref(gdy), _lib.stream_ptr()))
-        self._parity ^= 1
-        cur.wait_event(self._ev_reduced)
-        self._mark("exchange")
+        check(_lib.load().rdg_sh_grad_views(C.byref(sc_s), self.sh_degree, v_total, ptr(viewmats_all), ptr(basis_all),
+                                            ptr(dcolor_all), 1.0 / v_total, C.byref(gst), C.byref(gdy),
+                                            self._sm_queue[4:].data_ptr() if partitioned else None, _lib.stream_ptr()))
+
+    def materialize_sh_grads(self):
+        """After exchange_grads(defer_sh=True): write dL/dSH of the step into self.grads after all (what exchange_grads does
+        by default).  The deferred factors stay pending for the optimiser."""
+        d = getattr(self, "_deferred", None)
+        if d is None:
+            raise RuntimeError("no deferred SH gradient: call exchange_grads(defer_sh=True) first")
+        self._sh_from_factors(d["viewmats"], d["basis"], d["dcolor"], d["views"])
+
+    def _sh_adam_from_factors(self, tag: str, iteration: int, grad_scale: float):
+        """Adam of model `tag`'s f_dc / f_rest groups straight from the deferred factors (rdg_sh_adam_views)."""
+        d = self._deferred
+        opt = self.optim[tag]
+        lr = opt.lrs.group_lrs(iteration, opt.spatial_lr_scale)
+        a = _lib.RdgShAdam()
+        (m_dc, v_dc), (m_rest, v_rest) = opt.moments("f_dc"), opt.moments("f_rest")
+        a.exp_avg_dc, a.exp_avg_sq_dc, a.exp_avg_rest, a.exp_avg_sq_rest = ptr(m_dc), ptr(v_dc), ptr(m_rest), ptr(v_rest)
+        a.lr_dc, a.lr_rest, a.step = lr["f_dc"], lr["f_rest"], opt.steps + 1
+        sc_s = self._factor_scene(d["basis"])
+        none = C.POINTER(_lib.RdgShAdam)()
+        check(_lib.load().rdg_sh_adam_views(C.byref(sc_s), self.sh_degree, d["views"], ptr(d["viewmats"]), ptr(d["basis"]),
+                                            ptr(d["dcolor"]), float(grad_scale) / d["views"],
+                                            C.byref(a) if tag == "static" else none, C.byref(a) if tag == "dynamic" else none,
+                                            opt.betas[0], opt.betas[1], opt.eps, _lib.stream_ptr()))
 
     # -- motion-basis MLP (SURVEY.md §8 a1) ----------------------------------------------------------------
     def attach_basis_mlp(self, mlp, train_times: torch.Tensor, lr: float = 1.6e-3):
@@ -570,9 +669,18 @@ class SplatTrainStep:
         The reference densifies BEFORE optimizer.step() in the same iteration (rodygs.py:343-364); densification re-creates
         every nn.Parameter of the model, their .grad is None, and torch.optim.Adam skips them - so on a densification
         iteration that model's step is a no-op (no update, no step count).  densify_and_prune() arms the same skip here."""
+        d = getattr(self, "_deferred", None)
+        fused_sh = d is not None and tag in d["pending"]
+        if fused_sh:
+            d["pending"].discard(tag)
         if tag in self._skip_step:
             self._skip_step.discard(tag)
             return None
+        if fused_sh and (self.ns if tag == "static" else self.nd) > 0:
+            # exchange_grads(defer_sh=True): the SH groups step from the gathered factors - first, because the directions are
+            # evaluated from the means / motion coefficients that the second launch moves
+            self._sh_adam_from_factors(tag, iteration, grad_scale)
+            return self.optim[tag].step(self.params, self.grads, iteration, grad_scale, skip=("f_dc", "f_rest"))
         return self.optim[tag].step(self.params, self.grads, iteration, grad_scale)
 
     def enable_densification(self, tag: str):

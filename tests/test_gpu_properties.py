@@ -208,6 +208,74 @@ def test_factored_sh_exchange_equals_direct_sum_over_views():
         assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-12, name
 
 
+def test_fused_sh_adam_from_factors_equals_materialised_gradient_then_adam():
+    """exchange_grads(defer_sh=True) + optimizer_step (rdg_sh_adam_views: dL/dSH rebuilt per chunk in shared memory and
+    consumed by Adam) moves the parameters and both moments exactly like the default path (rdg_sh_grad_views writes
+    dL/dSH, rdg_adam_groups steps every group) - over two iterations, so the second step sees non-zero moments, with a
+    Gaussian count that is not a multiple of the 256-Gaussian chunk and per-model step counts / learning rates."""
+    from rodygs_b200.optim import GaussianLRs
+    N, H, W, T, VIEWS = 30_011, 128, 192, 6, 2
+    scene = synthetic.to_device(synthetic.make_scene(N, H, W, T, seed=11), "cuda")
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    cams = [synthetic.make_camera(v, 8, H, W, T) for v in range(VIEWS)]
+    gts = [(torch.rand(3, H, W, device="cuda", generator=gen), torch.rand(1, H, W, device="cuda", generator=gen)) for _ in cams]
+
+    def train(defer):
+        step = SplatTrainStep(scene, H, W, sh_degree=3, w_pearson=0.05, w_alpha=0.01, w_local=0.0)
+        step.attach_optimizer("static", GaussianLRs())
+        step.attach_optimizer("dynamic", GaussianLRs(scaling_lr=0.001, motion_coeff_lr=1.6e-4, feature_lr=0.004))
+        step.enable_factored_exchange(views_per_rank=VIEWS, world_size=1)
+        for it in (1, 2):
+            step.grads.zero_()
+            vms, bts = [], []
+            for slot, (cam, (gt, gtd)) in enumerate(zip(cams, gts)):
+                vm = cam.world_view_transform.t().contiguous().cuda()
+                pm = cam.projection_matrix.t().contiguous().cuda()
+                bt = step.p("table")[cam.time_index].clone()
+                step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, bt, gt, gtd, accumulate=slot > 0, dcolor_slot=slot)
+                vms.append(vm); bts.append(bt)
+            step.exchange_grads(torch.stack(vms).contiguous(), torch.stack(bts).contiguous(), defer_sh=defer)
+            if defer and it == 1:
+                # the deferred factors rebuild the same dL/dSH on demand
+                step.materialize_sh_grads()
+                assert step.g("static.features_rest").abs().max().item() > 0
+            step.optimizer_step("static", it)
+            if it == 2:
+                step.optimizer_step("dynamic", it)      # the dynamic model joins late: its own step count is 1
+        torch.cuda.synchronize()
+        return step
+
+    try:
+        engine.config.deterministic = True      # bit-identical gradients in both runs: what is compared is the optimiser path
+        a, b = train(False), train(True)
+    finally:
+        engine.config.deterministic = False
+    assert b._deferred is not None and not b._deferred["pending"]
+    moved = (a.params - synthetic_flat(a, scene)).abs().max().item()
+    assert moved > 0
+    for name in ("static.features_dc", "static.features_rest", "dynamic.features_dc", "dynamic.features_rest", "static.xyz",
+                 "dynamic.xyz", "motion_coeff"):
+        o, shp = a.layout[name]
+        n = 1
+        for d in shp:
+            n *= d
+        pa, pb = a.params[o:o + n], b.params[o:o + n]
+        # same gradient bits, same update formula; the two kernels may contract the moment updates into FMAs differently
+        assert (pa - pb).abs().max().item() <= 1e-6, name
+        tag = name.split(".")[0] if "." in name else "dynamic"
+        for ma, mb in zip((a.optim[tag].exp_avg, a.optim[tag].exp_avg_sq), (b.optim[tag].exp_avg, b.optim[tag].exp_avg_sq)):
+            xa, xb = ma[o:o + n], mb[o:o + n]
+            assert (xa - xb).abs().max().item() <= 1e-4 * xa.abs().max().item() + 1e-20, name
+    # the SH parameters really were stepped by the fused kernel (their gradient buffer was never written in run b, iteration 2)
+    o, shp = b.layout["dynamic.features_rest"]
+    assert b.optim["dynamic"].exp_avg[o:o + 45 * b.nd].abs().max().item() > 0
+
+
+def synthetic_flat(step, scene):
+    """the flat parameter buffer a fresh SplatTrainStep builds from `scene`"""
+    return SplatTrainStep(scene, step.H, step.W, sh_degree=step.sh_degree).params
+
+
 def test_deterministic_mode_is_bit_reproducible_and_agrees_with_the_default():
     """engine.config.deterministic (RDG_DETERMINISTIC=1): every gradient of the fused path is bit-identical run to run
     (integer accumulation of the blend partials, one CTA for the cross-CTA sums), and equals the default float-atomic

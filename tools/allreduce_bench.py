@@ -20,6 +20,7 @@ res = []
 for n in sizes:
     x = torch.randn(n, device="cuda")
     res.append((f"NCCL all_reduce AVG {n * 4 / 1e6:.0f} MB [{os.environ.get('NCCL_ALGO', 'default')}/{os.environ.get('NCCL_PROTO', 'default')}]", timeit(lambda: dist.all_reduce(x, op=dist.ReduceOp.AVG))))
+    res.append((f"NCCL all_reduce SUM {n * 4 / 1e6:.0f} MB", timeit(lambda: dist.all_reduce(x, op=dist.ReduceOp.SUM))))
 if os.environ.get("SYMM", "1") == "1":
     group = dist.group.WORLD
     try:
@@ -28,12 +29,24 @@ if os.environ.get("SYMM", "1") == "1":
         buf.normal_()
         for n in sizes:
             v = buf[:n]
-            for name, fn in (("multimem_all_reduce_", lambda: torch.ops.symm_mem.multimem_all_reduce_(v, "sum", group.group_name)),
-                             ("two_shot_all_reduce_", lambda: torch.ops.symm_mem.two_shot_all_reduce_(v, "sum", group.group_name))):
+            for name, fn in (("multimem_all_reduce_", lambda: torch.ops.symm_mem.multimem_all_reduce_(v, "sum", group.group_name)),):
                 try:
                     res.append((f"symm_mem {name} {n * 4 / 1e6:.0f} MB", timeit(fn)))
                 except Exception as e:
                     res.append((f"symm_mem {name} {n * 4 / 1e6:.0f} MB: {type(e).__name__}: {str(e)[:100]}", float("nan")))
+        # the repo's own in-switch kernel (rdg_allreduce_multimem) over the same buffer, bracketed by the barriers the trainer uses
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from rodygs_b200 import _lib
+        lib = _lib.load()
+        for unroll in (4, 8):
+            _lib.set_tunable("ar_unroll", unroll)
+            for ctas in (16, 32, 64, 128):
+                for n in sizes:
+                    def own():
+                        hdl.barrier(channel=0)
+                        _lib.check(lib.rdg_allreduce_multimem(int(hdl.multicast_ptr), n, rank, world, 1.0 / world, ctas, _lib.stream_ptr()))
+                        hdl.barrier(channel=0)
+                    res.append((f"rdg_allreduce_multimem {n * 4 / 1e6:.0f} MB, {ctas} CTAs x 512, unroll {unroll} (+2 barriers)", timeit(own)))
         if rank == 0:
             print("multicast_ptr", hex(hdl.multicast_ptr) if hdl.multicast_ptr else None, "signal pads", len(hdl.signal_pad_ptrs))
     except Exception as e:

@@ -9,7 +9,7 @@ from rodygs_b200.trainer import SplatTrainStep
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-N, H, W, T = 120_000, 256, 384, 10
+N, H, W, T = 320_000, 256, 384, 10      # > 264 chunks per model: the SM-partitioned backward engages
 scene = synthetic.to_device(synthetic.make_scene(N, H, W, T, seed=1), "cuda")
 step = SplatTrainStep(scene, H, W, w_pearson=0.05, w_alpha=0.01, w_local=0.0)
 gen = torch.Generator(device="cuda").manual_seed(5)
@@ -25,8 +25,9 @@ for v in range(world):
     run_view(v)
     ref += step.grads
 ref /= world
-for mode in ("multicast", "copy-engine"):
-    step.enable_factored_exchange(1, world, multicast=(mode == "multicast"))
+for mode, ar in (("multicast", "nccl"), ("copy-engine", "nccl"), ("copy-engine", "multimem"), ("copy-engine", "symm_op")):
+    step.enable_factored_exchange(1, world, multicast=(mode == "multicast"), allreduce=ar)
+    mode = f"{mode}/{ar}->{step._ar_mode}"
     vm_all = torch.stack([c.world_view_transform.t().contiguous() for c in cams]).cuda().contiguous()
     bt_all = torch.stack([step.p("table")[c.time_index] for c in cams]).contiguous()
     for rep in range(3):   # several steps: exercises the double-buffered factors
@@ -44,6 +45,31 @@ for mode in ("multicast", "copy-engine"):
         if rank == 0 or err > 1e-4:
             print(f"[rank {rank}] {mode} step {rep}: max rel err vs sequential mean {err:.2e}; vs rank 0 {same:.2e}; mc={bool(step._mc_base)}", flush=True)
         assert err < 2e-4 and same < 1e-5, (mode, rep, err, same)
+# deferred dL/dSH: the SH groups step from the gathered factors (rdg_sh_adam_views); parameters and moments must equal the
+# materialised path's and be identical on every rank
+from rodygs_b200.optim import GaussianLRs
+from rodygs_b200 import engine
+def train(defer):
+    st = SplatTrainStep(scene, H, W, w_pearson=0.05, w_alpha=0.01, w_local=0.0)
+    st.attach_optimizer("static", GaussianLRs()); st.attach_optimizer("dynamic", GaussianLRs(motion_coeff_lr=1.6e-4))
+    st.enable_factored_exchange(1, world)
+    for it in (1, 2):
+        c = cams[rank]
+        st.forward_backward(c.world_view_transform.t().contiguous().cuda(), c.projection_matrix.t().contiguous().cuda(), c.tanfovx,
+                            c.tanfovy, st.p("table")[c.time_index].contiguous(), gts[rank][0], gts[rank][1], dcolor_slot=0)
+        st.exchange_grads(vm_all, torch.stack([st.p("table")[c.time_index] for c in cams]).contiguous(), defer_sh=defer)
+        st.optimizer_step("static", it); st.optimizer_step("dynamic", it)
+    torch.cuda.synchronize()
+    return st
+engine.config.deterministic = True
+a, b = train(False), train(True)
+engine.config.deterministic = False
+o = sh_start(a.layout)
+dp = float((a.params[o:] - b.params[o:]).abs().max()); dm = float((a.optim["static"].exp_avg[o:] - b.optim["static"].exp_avg[o:]).abs().max())
+p0 = b.params.clone(); dist.broadcast(p0, 0)
+same = float((b.params - p0).abs().max())
+print(f"[rank {rank}] deferred SH Adam: max |dparam| vs materialised {dp:.2e}, |dm| {dm:.2e}; vs rank 0 {same:.2e}", flush=True)
+assert dp < 1e-5 and same == 0.0, (dp, same)
 dist.barrier()
 if rank == 0:
     print("dp_check OK")

@@ -61,7 +61,7 @@ def sh_kernel():
     sc_s = engine._scene_struct(scene_a)
     gst, gdy = engine._setgrad_struct(step._setgrad("static")), engine._setgrad_struct(step._setgrad("dynamic"))
     _lib.check(lib.rdg_sh_grad_views(C.byref(sc_s), 3, world, vm.data_ptr(), bt.data_ptr(), step.dcolor_all.data_ptr(), 1.0 / world,
-                                     C.byref(gst), C.byref(gdy), _lib.stream_ptr()))
+                                     C.byref(gst), C.byref(gdy), None, _lib.stream_ptr()))
 res["rdg_sh_grad_views (%d views)" % world] = timeit(sh_kernel)
 # timeline of two overlapped exchanges (kernel start/end per stream)
 from torch.profiler import profile, ProfilerActivity

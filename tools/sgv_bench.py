@@ -22,7 +22,7 @@ sc_s = engine._scene_struct(sc)
 gst, gdy = engine._setgrad_struct(step._setgrad("static")), engine._setgrad_struct(step._setgrad("dynamic"))
 def run():
     _lib.check(lib.rdg_sh_grad_views(C.byref(sc_s), 3, V, vm.data_ptr(), bt.data_ptr(), step.dcolor_all.data_ptr(), 1.0 / V,
-                                     C.byref(gst), C.byref(gdy), _lib.stream_ptr()))
+                                     C.byref(gst), C.byref(gdy), None, _lib.stream_ptr()))
 for _ in range(3): run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
