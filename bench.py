@@ -316,7 +316,9 @@ def run_ours(args, rank, world, local_rank):
     if factored:
         step.enable_factored_exchange(views_per_rank=1, world_size=world, copy_engine_gather=not args.nccl_gather,
                                       bucketed=not args.no_bucketed, sm_reserve=args.sm_reserve, multicast=args.multicast,
-                                      sm_partition=not args.no_sm_partition, allreduce=args.allreduce, allreduce_ctas=args.allreduce_ctas)
+                                      sm_partition=not args.no_sm_partition, allreduce=args.allreduce, allreduce_ctas=args.allreduce_ctas,
+                                      bwd_parts=args.bwd_parts, bwd_order=args.bwd_order,
+                                      bwd_parts_static=args.bwd_parts_static)
         for j in range(len(my_views)):
             cs = [synthetic.make_camera(r + j * world, n_views, H, W, T) for r in range(world)]
             all_vm.append(torch.stack([c.world_view_transform.t().contiguous() for c in cs]).to(dev).contiguous())
@@ -572,7 +574,10 @@ def run_ours(args, rank, world, local_rank):
                    "sample_value": rate}
         if factored:
             parallelism = (f"dp{world} (view-sharded; all-gather of the 12 B/Gaussian factors of dL/dSH + allreduce of the other gradients"
-                           + ("" if args.no_bucketed else f" per model under the other model's backward kernel, {args.sm_reserve} SMs left to NCCL")
+                           + ("" if args.no_bucketed else
+                              (f" by the in-switch kernel rdg_allreduce_multimem, pipelined under the per-Gaussian backward ({len(step._bwd_plan)} launches, order {args.bwd_order}), "
+                               f"{args.sm_reserve} SMs left to it" if step._ar_mode == "multimem" and step._bwd_plan is not None else
+                               f" ({step._ar_mode}) per model under the other model's backward kernel, {args.sm_reserve} SMs left to the collective"))
                            + (", dL/dSH kept factored for the SH groups' fused Adam (rdg_sh_adam_views) - not materialised in the timed step)"
                               if defer_sh else ", dL/dSH rebuilt per rank)"))
         else:
@@ -697,9 +702,13 @@ def main():
     ap.add_argument("--timeline", default="", help="write the kernel timeline of one step (rank 0, torch.profiler) to this file")
     ap.add_argument("--no-sm-partition", action="store_true",
                     help="N>1: size the persistent backward grids for 148 - sm_reserve SMs instead of the SM-partitioned chunk queue (A/B)")
-    ap.add_argument("--allreduce", default="nccl", choices=["nccl", "multimem", "symm_op"],
+    ap.add_argument("--bwd-parts", type=int, default=0,
+                    help="N>1, --allreduce multimem: launches of the dynamic model's per-Gaussian backward (pipelined exchange); 0: one bucket per model")
+    ap.add_argument("--allreduce", default="multimem", choices=["nccl", "multimem", "symm_op"],
                     help="N>1: all-reduce of the non-SH gradient range: NCCL, the in-switch kernel rdg_allreduce_multimem, or torch's symm_mem op")
     ap.add_argument("--allreduce-ctas", type=int, default=32)
+    ap.add_argument("--bwd-parts-static", type=int, default=2)
+    ap.add_argument("--bwd-order", default="sdt", help="N>1 pipelined exchange: order of the static launch (s), the dynamic launches (d) and the dL/dtable reduction (t)")
     ap.add_argument("--materialize-sh", action="store_true",
                     help="N>1: rebuild dL/dSH of all views in the timed step (rdg_sh_grad_views) instead of leaving the factors to the fused SH Adam")
     ap.add_argument("--plain-allreduce", action="store_true",

@@ -155,12 +155,16 @@ typedef struct RdgSceneGrad {
     float* table;            /* [T,num_basis,7] accumulated (+=) */
     float* basis_t;          /* [num_basis,7]   accumulated (+=) */
     float* g7_scratch;       /* [n_dynamic,8] scratch, required when scene.frame_order is set */
-    int32_t models;          /* 0 or 3: both models; 1: the static model only; 2: the dynamic model only (+ dL/dtable, dL/dB(t)).
-                              * The data-parallel step calls rdg_preprocess_bwd once per model so that the all-reduce of the
-                              * first model's gradient range runs under the second model's kernel (viewmatrix accumulates). */
-    uint32_t* sm_queue;      /* optional device scratch, 4 uint32: with the "sm_reserve" tunable > 0 the persistent kernel then runs
-                              * SM-partitioned - CTAs that land on the reserved SMs exit, the others draw chunks from this counter -
-                              * so that a collective on another stream finds free SMs while it runs */
+    int32_t models;          /* 0 or 3: both models; 1: the static model only; 2: the dynamic model only.
+                              * The data-parallel step calls rdg_preprocess_bwd once per model (or per part of a model) so that the
+                              * all-reduce of the ranges already written runs under the next launch (viewmatrix accumulates). */
+    int32_t part, parts;     /* parts > 1: only the part-th of `parts` equal pieces of the selected chunk range (256-Gaussian chunks:
+                              * piece boundaries are multiples of 256 rows of the model); 0 / 0 = everything */
+    int32_t dtable_mode;     /* dL/dtable + dL/dB(t) reduction over the birth-frame CSR (needs every dynamic part's g7 rows):
+                              * 0 = after the dynamic model's last part (default), 1 = skip, 2 = ONLY it (no per-Gaussian kernel) */
+    uint32_t* sm_queue;      /* optional device scratch, 4 uint32, ZERO on first use (the kernel leaves it zero): with the "sm_reserve"
+                              * tunable > 0 the persistent kernel then runs SM-partitioned - CTAs that land on the reserved SMs exit,
+                              * the others draw chunks from this counter - so that a collective on another stream finds free SMs */
     float* dcolor;           /* optional [N,3]: dL/d(rgb) of every Gaussian after the SH clamp mask (zeros when it is not
                               * visible) - the 12-byte factors from which rdg_sh_grad_views rebuilds dL/dSH of all views
                               * of a data-parallel step; pass st/dy.sh_dc = sh_rest = NULL with it to skip the dSH rows */
@@ -280,6 +284,10 @@ int rdg_sh_adam_views(const RdgScene* scene, int32_t sh_degree, int32_t n_views,
  * The caller puts a cross-rank barrier on the stream before (all ranks' values written) and after (all slices landed).  Needs
  * NVSwitch multicast (NVLS); the fallback is the NCCL all-reduce of the same range. */
 int rdg_allreduce_multimem(float* mc_range, int64_t n_floats, int32_t rank, int32_t world, float scale, int32_t ctas, void* stream);
+/* ... of up to 8 ranges of the same buffer in one launch (the structure-of-arrays fields of one slice of Gaussians):
+ * offsets / lens in floats from mc_base (host arrays), every range 16-byte aligned and a multiple of 4 floats. */
+int rdg_allreduce_multimem_ranges(float* mc_base, const int64_t* offsets, const int64_t* lens, int32_t n_ranges, int32_t rank,
+                                  int32_t world, float scale, int32_t ctas, void* stream);
 
 /* ---- losses ----------------------------------------------------------------- */
 

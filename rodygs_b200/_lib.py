@@ -59,7 +59,8 @@ class RdgSetGrad(C.Structure):
 class RdgSceneGrad(C.Structure):
     _fields_ = [("st", RdgSetGrad), ("dy", RdgSetGrad), ("colors_precomp", c_ptr), ("means2D", c_ptr),
                 ("viewmatrix", c_ptr), ("motion_coeff", c_ptr), ("table", c_ptr), ("basis_t", c_ptr), ("g7_scratch", c_ptr),
-                ("models", C.c_int32), ("sm_queue", c_ptr), ("dcolor", c_ptr)]
+                ("models", C.c_int32), ("part", C.c_int32), ("parts", C.c_int32), ("dtable_mode", C.c_int32),
+                ("sm_queue", c_ptr), ("dcolor", c_ptr)]
 
 
 class RdgDensifyField(C.Structure):
@@ -125,6 +126,8 @@ SYMBOLS = {
     "rdg_sh_adam_views": (C.c_int, [C.POINTER(RdgScene), C.c_int32, C.c_int32, c_ptr, c_ptr, c_ptr, C.c_float,
                                     C.POINTER(RdgShAdam), C.POINTER(RdgShAdam), C.c_float, C.c_float, C.c_float, c_ptr]),
     "rdg_allreduce_multimem": (C.c_int, [c_ptr, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_int32, c_ptr]),
+    "rdg_allreduce_multimem_ranges": (C.c_int, [c_ptr, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_int32,
+                                                C.c_float, C.c_int32, c_ptr]),
     "rdg_l1_dssim_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "rdg_l1_dssim": (C.c_int, [c_ptr, c_ptr, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, c_ptr, c_ptr,
                                c_ptr, C.c_int64, c_ptr]),

@@ -119,3 +119,18 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 #endif
+
+// SM-partitioned persistent kernels (preprocess_bwd.cu, sh_grad_views.cu): q[0] is the chunk counter, q[1] counts the CTAs
+// that are done with it.  Called by one thread of EVERY CTA of the grid once it will not touch the queue again; the last one
+// zeroes both words, so the next launch finds a clean queue without a memset between the kernels (a stream-ordered memset
+// costs ~10 us of idle GPU per launch - the pipelined exchange launches six of these kernels back to back).
+#ifdef __CUDACC__
+__device__ __forceinline__ void rdg_queue_release(uint32_t* q, unsigned n_ctas) {
+    __threadfence();
+    if (atomicAdd(q + 1, 1u) == n_ctas - 1u) {
+        q[0] = 0u;
+        q[1] = 0u;
+        __threadfence();
+    }
+}
+#endif

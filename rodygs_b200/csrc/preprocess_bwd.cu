@@ -72,7 +72,10 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
     if (p.sm_queue) {                         // leave the upper SMs to NCCL (a persistent grid cannot be pinned, but it can decline)
         unsigned smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
-        if ((int)smid >= p.sm_limit) return;
+        if ((int)smid >= p.sm_limit) {
+            if (threadIdx.x == 0) rdg_queue_release(p.sm_queue, gridDim.x);
+            return;
+        }
     }
     const bool use_sh = sc.colors_precomp == nullptr;
     const bool deform = RAW && sc.use_deform && sc.n_dynamic > 0;
@@ -441,6 +444,7 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
         chunk_nx = chunk_after;
     }
     if (threadIdx.x == 0 && store_pending) rdg_bulk_store_wait_read();
+    if (queued && threadIdx.x == 0) rdg_queue_release(p.sm_queue, gridDim.x);
 
     // ---- pose gradient: warp shuffle -> shared -> one atomic set per CTA ----
     if (p.gr.viewmatrix) {
@@ -660,26 +664,38 @@ extern "C" int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, co
     p.sm_limit = 0;
     p.c_begin = do_static ? 0 : cs_h;
     p.c_end = do_dynamic ? cs_h + cd_h : cs_h;
-    const int64_t chunks = p.c_end - p.c_begin;
-    if (chunks <= 0) return RDG_OK;
+    RDG_CHECK_ARG(grads->parts >= 0 && grads->part >= 0 && (grads->parts == 0 ? grads->part == 0 : grads->part < grads->parts), "bad part / parts");
+    RDG_CHECK_ARG(grads->dtable_mode >= 0 && grads->dtable_mode <= 2, "dtable_mode must be 0..2");
+    const bool last_part = grads->parts <= 1 || grads->part == grads->parts - 1;
+    if (grads->parts > 1) {
+        const int64_t all = p.c_end - p.c_begin, per = (all + grads->parts - 1) / grads->parts;
+        const int64_t b = p.c_begin + per * grads->part, e = b + per;
+        p.c_begin = b < p.c_end ? b : p.c_end;
+        p.c_end = e < p.c_end ? e : p.c_end;
+    }
+    const bool run_dtable = csr && grads->table && ((grads->dtable_mode == 0 && do_dynamic && last_part) || grads->dtable_mode == 2);
+    const int64_t chunks = grads->dtable_mode == 2 ? 0 : p.c_end - p.c_begin;
+    if (chunks <= 0 && !run_dtable) return RDG_OK;
     // 2 CTAs per SM (register-limited), persistent; "sm_reserve" leaves SMs to a collective running beside this kernel
     int sms = RDG_SM_COUNT - rdg_tunable(RDG_TUN_SM_RESERVE);
     if (sms < 8) sms = 8;
     const int64_t cap = (int64_t)sms * 2;
     int grid = (int)(chunks < cap ? chunks : cap);
+    if (grid < 1) grid = 1;
     cudaStream_t s = (cudaStream_t)stream;
     if (grads->sm_queue && sms < RDG_SM_COUNT && chunks > cap && rdg_tunable(RDG_TUN_DETERMINISTIC) == 0) {
         // SM-partitioned mode: a full-machine grid whose CTAs on SMs >= sms exit at once; the others share a chunk queue
-        RDG_CUDA(cudaMemsetAsync(grads->sm_queue, 0, 4 * sizeof(uint32_t), s));
-        p.sm_queue = grads->sm_queue;
+        p.sm_queue = grads->sm_queue;      // zero on entry, left zero by the kernel (rdg_queue_release)
         p.sm_limit = sms;
         grid = RDG_SM_COUNT * 2;
     }
-    const int rc = scene->raw ? launch_bwd_deg<true>(p, view->sh_degree, grid, smem, s)
-                              : launch_bwd_deg<false>(p, view->sh_degree, grid, smem, s);
-    if (rc) return rc;
-    rdg_count_launches(1);
-    if (csr && grads->table && do_dynamic) {
+    if (chunks > 0) {
+        const int rc = scene->raw ? launch_bwd_deg<true>(p, view->sh_degree, grid, smem, s)
+                                  : launch_bwd_deg<false>(p, view->sh_degree, grid, smem, s);
+        if (rc) return rc;
+        rdg_count_launches(1);
+    }
+    if (run_dtable) {
         if (rdg_tunable(RDG_TUN_DTABLE_V1) != 0) {
             const dim3 g(scene->num_times, DT_SLICES);
             dtable_kernel<<<g, 128, 0, s>>>(scene->frame_order, scene->frame_offsets, scene->motion_coeff, grads->g7_scratch,

@@ -79,7 +79,10 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) sh_grad_views_kernel(const ShGra
     if (p.sm_queue) {
         unsigned smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
-        if ((int)smid >= p.sm_limit) return;
+        if ((int)smid >= p.sm_limit) {
+            if (threadIdx.x == 0) rdg_queue_release(p.sm_queue, gridDim.x);
+            return;
+        }
     }
     __shared__ long long q_s[2];
     float* sh_s = smem;                                   // [256][SH_ROW]
@@ -279,6 +282,7 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) sh_grad_views_kernel(const ShGra
         chunk = queued ? q_s[q_par] : chunk + (long long)gridDim.x;
     }
     if (threadIdx.x == 0 && store_pending) rdg_bulk_store_wait_read();
+    if (queued && threadIdx.x == 0) rdg_queue_release(p.sm_queue, gridDim.x);
 }
 
 // dcolor[i] = acc[i][6..8] with the channels the forward pass clamped at zero masked out: the factors of dL/dSH,
@@ -430,8 +434,7 @@ extern "C" int rdg_sh_grad_views(const RdgScene* scene, int32_t sh_degree, int32
     int grid = (int)(chunks < cap ? chunks : cap);
     cudaStream_t s = (cudaStream_t)stream;
     if (sm_queue && sms < RDG_SM_COUNT && chunks > cap) {
-        RDG_CUDA(cudaMemsetAsync(sm_queue, 0, 4 * sizeof(uint32_t), s));
-        p.sm_queue = sm_queue;
+        p.sm_queue = sm_queue;             // zero on entry, left zero by the kernel (rdg_queue_release)
         p.sm_limit = sms;
         grid = RDG_SM_COUNT * 2;
     }

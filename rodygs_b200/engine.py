@@ -386,13 +386,15 @@ def _setgrad_struct(g: SetGrads) -> RdgSetGrad:
 
 
 def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: SceneGrads, stage_hook=None,
-                    after_blend=None, after_model=None):
+                    after_blend=None, after_model=None, bwd_plan=None):
     """blend backward -> preprocess backward.  Writes into the tensors of `grads`.
     after_blend: data-parallel mode - called as soon as grads.dcolor (the factors of dL/dSH) is final, i.e.
     right after the blend backward, so that their all-gather overlaps the per-Gaussian backward.
     after_model: data-parallel mode - the per-Gaussian backward runs as one launch per model (dynamic first: it is the
     larger gradient range) and after_model("dynamic") / after_model("static") is called right after each, so that the
-    all-reduce of one model's range runs under the other model's kernel."""
+    all-reduce of one model's range runs under the other model's kernel.
+    bwd_plan: a finer schedule for the same - a sequence of (models, part, parts, dtable_mode, piece) launches
+    (RdgSceneGrad.models / part / parts / dtable_mode); after_model(piece) is called after each."""
     lib = _lib.load()
     dev = state.view.viewmatrix.device
     stream = _lib.stream_ptr()
@@ -451,16 +453,18 @@ def render_backward(state: FwdState, dL_dcolor, dL_ddepth, dL_dalpha, grads: Sce
         g.g7_scratch = ptr(grads.g7_scratch)
     ns, nd = state.scene.counts()
     if after_model is not None and ns > 0 and nd > 0:
-        for models, tag in ((2, "dynamic"), (1, "static")):
-            g.models = models
+        # (models, part, parts, dtable_mode, piece name): one launch per piece, after_model(piece) after each
+        plan = bwd_plan or ((2, 0, 1, 0, "dynamic"), (1, 0, 1, 0, "static"))
+        for models, part, parts, dtable_mode, piece in plan:
+            g.models, g.part, g.parts, g.dtable_mode = models, part, parts, dtable_mode
             check(lib.rdg_preprocess_bwd(C.byref(sc_s), C.byref(vw_s), C.byref(gm_s), ptr(acc), C.byref(g), stream))
-            after_model(tag)
+            after_model(piece)
     else:
         g.models = 0
         check(lib.rdg_preprocess_bwd(C.byref(sc_s), C.byref(vw_s), C.byref(gm_s), ptr(acc), C.byref(g), stream))
         if after_model is not None:
-            after_model("dynamic" if nd > 0 else "static")
-            after_model("static" if nd > 0 else "dynamic")
+            for piece in ("dynamic", "static") if nd > 0 else ("static", "dynamic"):
+                after_model(piece)
     if stage_hook:
         stage_hook("preprocess_bwd")
     return acc

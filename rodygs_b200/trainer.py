@@ -328,7 +328,7 @@ class SplatTrainStep:
                     model_hook = self._after_model   # one view per rank: each model's range is final after its own launch
             engine.render_backward(state, self.dL_dcolor, self.dL_ddepth if use_depth else None,
                                    self.dL_dalpha if use_alpha else None, grads, stage_hook=self._mark, after_blend=hook,
-                                   after_model=model_hook)
+                                   after_model=model_hook, bwd_plan=self._bwd_plan if model_hook is not None else None)
         finally:
             self.grads = saved
         if accumulate:
@@ -343,7 +343,8 @@ class SplatTrainStep:
     # -- data-parallel exchange with factored SH gradients -----------------------------------------
     def enable_factored_exchange(self, views_per_rank: int, world_size: int, copy_engine_gather: bool = True,
                                  gather_streams: int = 4, bucketed: bool = True, sm_reserve: int = 16, multicast: bool = False,
-                                 sm_partition: bool = True, allreduce: str = "nccl", allreduce_ctas: int = 32):
+                                 sm_partition: bool = True, allreduce: str = "multimem", allreduce_ctas: int = 32, bwd_parts: int = 0,
+                                 bwd_order: str = "sdt", bwd_parts_static: int = 2):
         """Buffers and the side streams for exchange_grads(): the local factors [views_per_rank, N, 3], the gathered
         ones, and a communication stream on which the collectives overlap the backward kernels.
 
@@ -365,14 +366,20 @@ class SplatTrainStep:
         if self.views_per_rank * self.world_size > 16:
             raise ValueError("factored exchange: rdg_sh_grad_views stages at most 16 views per step (views_per_rank * world_size)")
         self._fx_args = (views_per_rank, world_size, copy_engine_gather, gather_streams, bucketed, sm_reserve, multicast, sm_partition,
-                         allreduce, allreduce_ctas)
+                         allreduce, allreduce_ctas, bwd_parts, bwd_order, bwd_parts_static)
         # sm_partition: the persistent per-Gaussian kernels launch a full-machine grid whose CTAs on the reserved SMs exit at once
         # (chunk queue, RdgSceneGrad.sm_queue) instead of a smaller grid that the hardware may place on any SM
         self._sm_partition = bool(sm_partition)
         # allreduce: how the non-SH gradient range is summed over the ranks.
         #   "nccl"      torch.distributed.all_reduce (ReduceOp.AVG: a ring; NCCL has no in-switch reduction for AVG)
-        #   "multimem"  the gradient buffer moves into symmetric memory and rdg_allreduce_multimem reduces it inside the NVLink
-        #               switch (multimem.ld_reduce + multimem.st, the 1 / world scale fused), bracketed by cross-rank barriers
+        #   "multimem"  (default; falls back to "nccl" without NVLS) the gradient buffer moves into symmetric memory and
+        #               rdg_allreduce_multimem reduces it inside the NVLink switch (multimem.ld_reduce + multimem.st, the
+        #               1 / world scale fused).  With bwd_parts > 0 the exchange is also PIPELINED: the per-Gaussian backward
+        #               runs as bwd_parts launches over the dynamic model + bwd_parts_static over the static model + the dL/dtable
+        #               reduction, and every piece's structure-of-arrays ranges are reduced (one launch) while the next piece is
+        #               computed.  Measured: 2.76 vs 2.87 ms/step on 2 GPUs, but 3.03-3.10 vs 2.98 ms on 8 (profiles/README.md:
+        #               there the NVLink ingress - 168 MB of factors + 94 MB of all-reduce per rank - is busy for the whole tail
+        #               either way and the extra launches / barriers only add to it), so it is off by default
         #   "symm_op"   torch.ops.symm_mem.multimem_all_reduce_ on the same buffer + a scaling pass (library kernel, A/B)
         import torch.distributed as dist
         self._ar_mode, self._ar_ctas = "nccl", int(allreduce_ctas)
@@ -442,9 +449,12 @@ class SplatTrainStep:
         self._bucketed = bool(bucketed) and self.world_size > 1 and self.ns > 0 and self.nd > 0
         self._buckets = {"static": (self.layout["static.xyz"][0], self.layout["dynamic.xyz"][0]),
                          "dynamic": (self.layout["dynamic.xyz"][0], sh_start(self.layout))}
-        self._ev_model = {t: torch.cuda.Event() for t in self._buckets}
-        self._ev_bucket = {t: torch.cuda.Event() for t in self._buckets}
+        self._ev_piece = {}
         self._buckets_started = 0
+        # pipelined exchange (in-switch all-reduce only: the pieces are structure-of-arrays slices, one launch each)
+        self._bwd_plan, self._bwd_pieces = None, None
+        if self._bucketed and self._ar_mode == "multimem" and int(bwd_parts) > 0:
+            self._bwd_plan, self._bwd_pieces = self._make_bwd_plan(int(bwd_parts), bwd_order, max(1, int(bwd_parts_static)))
         self._sm_queue = torch.zeros(8, dtype=torch.int32, device=self.dev)
         if self._bucketed:
             _lib.set_tunable("sm_reserve", int(sm_reserve))
@@ -478,16 +488,86 @@ class SplatTrainStep:
             self._ev_gathered.record(self.comm_stream)
         self._gather_started = True
 
-    def _after_model(self, tag: str):
-        """Called by engine.render_backward right after the per-Gaussian backward of model `tag`: all-reduce (mean over the
-        ranks) of that model's gradient range on the communication stream."""
-        lo, hi = self._buckets[tag]
-        self._ev_model[tag].record()
+    def _piece_ranges(self, tag: str, part: int, parts: int):
+        """Float ranges (offset, length) inside the flat buffers of the per-Gaussian gradients that the part-th of `parts`
+        launches of model `tag` writes (rdg_preprocess_bwd splits the model's 256-Gaussian chunks into equal runs)."""
+        n = self.ns if tag == "static" else self.nd
+        chunks = (n + 255) // 256
+        per = (chunks + parts - 1) // parts
+        g0, g1 = min(per * part, chunks) * 256, min(per * (part + 1), chunks) * 256
+        last = g1 >= n
+        g1 = min(g1, n)
+        fields = [(f"{tag}.xyz", 3), (f"{tag}.scaling", 3), (f"{tag}.rotation", 4), (f"{tag}.opacity", 1)]
+        if tag == "dynamic":
+            fields.append(("motion_coeff", self.num_basis))
+        out = []
+        for name, width in fields:
+            off = self.layout[name][0]
+            lo, hi = off + g0 * width, off + g1 * width
+            if last:
+                hi = (hi + 3) // 4 * 4          # the block is padded to 64 floats (zeros on every rank)
+            if hi > lo:
+                out.append((lo, hi - lo))
+        return out
+
+    def _make_bwd_plan(self, parts_dynamic: int, order: str = "sdt", parts_static: int = 1):
+        """Schedule of the per-Gaussian backward under the pipelined exchange: `order` is a permutation of s (static model,
+        `parts_static` launches), d (dynamic model, `parts_dynamic` launches) and t (the dL/dtable reduction, after d).  The all-reduce of a
+        piece starts as soon as it is written and runs under the following launches, so only the last piece's all-reduce is
+        exposed; the 45 KB table range rides on the next piece's launch when there is one."""
+        assert sorted(order) == ["d", "s", "t"] and order.index("d") < order.index("t"), order
+        plan, pieces, carry = [], {}, []
+        for ch in order:
+            if ch == "d":
+                for k in range(parts_dynamic):
+                    name = f"dynamic.{k}"
+                    plan.append((2, k, parts_dynamic, 1, name))
+                    pieces[name] = self._piece_ranges("dynamic", k, parts_dynamic) + carry
+                    carry = []
+            elif ch == "s":
+                for k in range(parts_static):
+                    name = f"static.{k}"
+                    plan.append((1, k, parts_static, 1, name))
+                    pieces[name] = self._piece_ranges("static", k, parts_static) + carry
+                    carry = []
+            else:
+                lo = self.layout["table"][0]
+                plan.append((2, 0, 1, 2, "table"))
+                if ch == order[-1]:
+                    pieces["table"] = [(lo, sh_start(self.layout) - lo)]
+                else:
+                    pieces["table"] = []            # reduced with the next piece
+                    carry = [(lo, sh_start(self.layout) - lo)]
+        return tuple(plan), pieces
+
+    def _after_model(self, piece: str):
+        """Called by engine.render_backward right after the launch that completes `piece` of the per-Gaussian gradients:
+        all-reduce (mean over the ranks) of that piece on the all-reduce stream."""
+        ev = self._ev_piece.get(piece)
+        if ev is None:
+            ev = self._ev_piece[piece] = torch.cuda.Event()
+        ev.record()
         with torch.cuda.stream(self.ar_stream):
-            self.ar_stream.wait_event(self._ev_model[tag])
-            self._allreduce_range(lo, hi)
-            self._ev_bucket[tag].record(self.ar_stream)
+            self.ar_stream.wait_event(ev)
+            if self._bwd_plan is None:
+                lo, hi = self._buckets[piece]
+                self._allreduce_range(lo, hi)
+            elif self._bwd_pieces[piece]:
+                self._allreduce_ranges(self._bwd_pieces[piece], final=(piece == self._bwd_plan[-1][4]))
         self._buckets_started += 1
+
+    def _allreduce_ranges(self, ranges, final: bool):
+        """In-switch mean over the ranks of several ranges of the symmetric gradient buffer (one launch).  The barrier in front
+        says every rank has written the ranges (and, for the next call, that the previous call's slices have landed); only
+        the last call of a step needs one behind it."""
+        hdl = self._grads_symm
+        n = len(ranges)
+        offs, lens = (C.c_int64 * n)(*[r[0] for r in ranges]), (C.c_int64 * n)(*[r[1] for r in ranges])
+        hdl.barrier(channel=0)
+        check(_lib.load().rdg_allreduce_multimem_ranges(int(hdl.multicast_ptr), offs, lens, n, self._ar_rank, self.world_size,
+                                                        1.0 / self.world_size, self._ar_ctas, _lib.stream_ptr()))
+        if final:
+            hdl.barrier(channel=0)
 
     def _allreduce_range(self, lo: int, hi: int):
         """Mean over the ranks of self.grads[lo:hi], on the current stream."""
@@ -526,8 +606,8 @@ class SplatTrainStep:
         if not self._gather_started:
             self._start_gather()
         self._gather_started = False
-        if self._buckets_started == 2:
-            # both model ranges are already in flight (or done) on the communication stream
+        if self._buckets_started == (2 if self._bwd_plan is None else len(self._bwd_plan)):
+            # every range is already in flight (or done) on the communication stream
             self._buckets_started = 0
             with torch.cuda.stream(self.ar_stream):
                 self._ev_reduced.record(self.ar_stream)

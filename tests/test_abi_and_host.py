@@ -39,7 +39,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(_lib.RdgBins) == 11 * 8
     assert C.sizeof(_lib.RdgImage) == 5 * 8
     assert C.sizeof(_lib.RdgSetGrad) == 6 * 8
-    assert C.sizeof(_lib.RdgSceneGrad) == 2 * 48 + 10 * 8
+    assert C.sizeof(_lib.RdgSceneGrad) == 2 * 48 + 11 * 8
     assert C.sizeof(_lib.RdgScene) == 16 + 2 * 56 + 8 + 8 + 16 + 4 * 8 + 8 + 2 * 8
     assert C.sizeof(_lib.RdgBasisMlp) == 6 * 4 + 7 * 8
     assert C.sizeof(_lib.RdgAdamGroup) == 24 and C.sizeof(_lib.RdgDensifyField) == 24

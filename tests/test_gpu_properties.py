@@ -4,7 +4,7 @@ identities, determinism of the forward pass and linearity of the backward pass."
 import pytest
 import torch
 
-from rodygs_b200 import engine, synthetic
+from rodygs_b200 import _lib, engine, synthetic
 from rodygs_b200.trainer import SplatTrainStep
 
 pytestmark = pytest.mark.gpu
@@ -206,6 +206,66 @@ def test_factored_sh_exchange_equals_direct_sum_over_views():
             n *= s
         a, b = got[o:o + n], ref[o:o + n]
         assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-12, name
+
+
+def test_backward_in_pieces_equals_one_launch_and_pieces_tile_the_reduced_range():
+    """The pipelined exchange runs the per-Gaussian backward as several launches (RdgSceneGrad.part / parts / dtable_mode:
+    dynamic model in 3 pieces, static model, dL/dtable reduction).  Together they write the same gradients as one launch,
+    and the float ranges the trainer all-reduces after each piece tile the non-SH range exactly once."""
+    from rodygs_b200.trainer import sh_start
+    N, H, W, T = 40_011, 128, 192, 6                       # 79 chunks per model: ragged last piece, ragged last chunk
+    scene = synthetic.to_device(synthetic.make_scene(N, H, W, T, seed=5), "cuda")
+    step = SplatTrainStep(scene, H, W, sh_degree=3, w_pearson=0.05, w_alpha=0.01, w_local=0.0)
+    cam = synthetic.make_camera(1, 8, H, W, T)
+    vm, pm = cam.world_view_transform.t().contiguous().cuda(), cam.projection_matrix.t().contiguous().cuda()
+    bt = step.p("table")[cam.time_index].clone()
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    gt, gtd = torch.rand(3, H, W, device="cuda", generator=gen), torch.rand(1, H, W, device="cuda", generator=gen)
+    n_plain = sh_start(step.layout)
+    try:
+        engine.config.deterministic = True
+        step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, bt, gt, gtd)
+        ref, ref_view = step.grads[:n_plain].clone(), step.view_grad.clone()
+        assert ref.abs().max().item() > 0
+        step.enable_factored_exchange(views_per_rank=1, world_size=1)
+        step.world_size, step._bucketed = 2, True      # take the data-parallel schedule on one GPU
+        step._bwd_plan, step._bwd_pieces = step._make_bwd_plan(3)
+        called = []
+        step._after_model = called.append
+        step._start_gather = lambda: None
+        step.grads.zero_()
+        step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, bt, gt, gtd, dcolor_slot=0)
+        torch.cuda.synchronize()
+        got_det, view_det = step.grads[:n_plain].clone(), step.view_grad.clone()
+        # ... and with the SM-partitioned kernels (chunk queue; 140 of the 148 SMs "reserved" so that 27 chunks exceed the grid):
+        # the queue cleans itself between the five launches, every chunk is processed exactly once
+        engine.config.deterministic = False
+        _lib.set_tunable("sm_reserve", 140)
+        for _ in range(2):
+            step.grads.zero_()
+            step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, bt, gt, gtd, dcolor_slot=0)
+        torch.cuda.synchronize()
+        assert int(step._sm_queue.abs().max()) == 0
+        got_q = step.grads[:n_plain].clone()
+    finally:
+        engine.config.deterministic = False
+        _lib.set_tunable("sm_reserve", 0)
+    assert float((got_q - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    step.grads[:n_plain].copy_(got_det)
+    step.view_grad.copy_(view_det)
+    assert called[:5] == ["static.0", "dynamic.0", "dynamic.1", "dynamic.2", "table"]
+    got = step.grads[:n_plain]
+    assert torch.equal(got, ref), float((got - ref).abs().max())
+    # the pose gradient is summed per launch and then across launches: same terms, different association
+    assert float((step.view_grad - ref_view).abs().max()) <= 1e-5 * float(ref_view.abs().max())
+    cover = torch.zeros(n_plain, dtype=torch.int32)
+    for piece in called[:5]:
+        for lo, ln in step._bwd_pieces[piece]:
+            assert lo % 4 == 0 and ln % 4 == 0 and lo + ln <= n_plain
+            cover[lo:lo + ln] += 1
+    assert int(cover.max()) == 1
+    nz = ref.cpu() != 0
+    assert bool((cover[nz] == 1).all())          # everything that can be non-zero is reduced exactly once
 
 
 def test_fused_sh_adam_from_factors_equals_materialised_gradient_then_adam():

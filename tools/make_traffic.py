@@ -8,7 +8,7 @@ import os
 import sys
 
 STAGE = {"preprocess_fwd_kernel": "preprocess_fwd", "tile_scan_kernel": "bin", "tile_place_kernel": "bin",
-         "tile_sort_kernel": "bin", "blend_fwd_kernel": "blend_fwd", "ssim_fwd_kernel": "loss", "ssim_bwd_kernel": "loss",
+         "tile_sort_kernel": "bin", "blend_fwd_kernel": "blend_fwd", "tile_split_kernel": "blend_fwd", "local_pearson_finalize_kernel": "loss", "ssim_fwd_kernel": "loss", "ssim_bwd_kernel": "loss",
          "loss_finalize_kernel": "loss", "blend_bwd_kernel": "blend_bwd", "preprocess_bwd_kernel": "preprocess_bwd",
          "dtable_kernel": "preprocess_bwd", "dtable2_kernel": "preprocess_bwd"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
