@@ -24,9 +24,9 @@ extern "C" uint64_t rdg_launch_count(void) { return g_launches.load(std::memory_
 // Tunables: A/B switches and test knobs of the launchers.  Initial values come from the environment (RDG_<NAME>),
 // rdg_set_tunable() overrides them at run time (tests use it to drive the multi-chunk paths of the persistent
 // kernels at sizes the CPU oracle can check).
-static const char* const g_tun_names[RDG_TUN_COUNT] = {"pre_grid_cap", "dtable_v1", "diff_smem", "deterministic", "sm_reserve", "ar_unroll"};
-static const char* const g_tun_env[RDG_TUN_COUNT] = {"RDG_PRE_GRID_CAP", "RDG_DTABLE_V1", "RDG_DIFF_SMEM", "RDG_DETERMINISTIC", "RDG_SM_RESERVE", "RDG_AR_UNROLL"};
-static const int g_tun_default[RDG_TUN_COUNT] = {0, 0, 1, 0, 0, 4};
+static const char* const g_tun_names[RDG_TUN_COUNT] = {"pre_grid_cap", "dtable_v1", "diff_smem", "deterministic", "sm_reserve", "ar_unroll", "l2_prefetch"};
+static const char* const g_tun_env[RDG_TUN_COUNT] = {"RDG_PRE_GRID_CAP", "RDG_DTABLE_V1", "RDG_DIFF_SMEM", "RDG_DETERMINISTIC", "RDG_SM_RESERVE", "RDG_AR_UNROLL", "RDG_L2_PREFETCH"};
+static const int g_tun_default[RDG_TUN_COUNT] = {0, 0, 1, 0, 0, 4, 0};
 static std::atomic<int> g_tun[RDG_TUN_COUNT];
 static std::atomic<bool> g_tun_init{false};
 

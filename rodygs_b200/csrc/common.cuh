@@ -10,7 +10,7 @@
 
 void rdg_set_error(const char* fmt, ...);
 void rdg_count_launches(int n);
-enum { RDG_TUN_PRE_GRID_CAP = 0, RDG_TUN_DTABLE_V1 = 1, RDG_TUN_DIFF_SMEM = 2, RDG_TUN_DETERMINISTIC = 3, RDG_TUN_SM_RESERVE = 4, RDG_TUN_AR_UNROLL = 5, RDG_TUN_COUNT = 6 };
+enum { RDG_TUN_PRE_GRID_CAP = 0, RDG_TUN_DTABLE_V1 = 1, RDG_TUN_DIFF_SMEM = 2, RDG_TUN_DETERMINISTIC = 3, RDG_TUN_SM_RESERVE = 4, RDG_TUN_AR_UNROLL = 5, RDG_TUN_L2_PREFETCH = 6, RDG_TUN_COUNT = 7 };
 // dynamic shared memory a preprocess CTA may ask for and still run 2 CTAs per SM (227 KB per SM, 1 KB reserved per CTA)
 #define RDG_PRE_SMEM_MAX ((size_t)112 * 1024)
 int rdg_tunable(int id);   // api.cu: environment default, rdg_set_tunable() override

@@ -30,6 +30,7 @@ struct PreBwdParams {
     int diff_smem;     // B(t) - table rows staged in shared memory (rdg_stage_diff)
     int dtab_atomic;   // no CSR: accumulate dL/dtable with global atomics from this kernel
     int64_t c_begin, c_end;   // chunk range of this launch (RdgSceneGrad.models: one model at a time under data parallelism)
+    int l2_prefetch;          // next chunk's parameter / accumulator rows prefetched into L2 (cp.async.bulk.prefetch.L2)
     uint32_t* sm_queue;       // non-NULL: SM-partitioned mode - CTAs that land on an SM >= sm_limit exit at once, the others take
     int sm_limit;             // chunks from this counter, so that SMs sm_limit.. stay FREE for a collective on another stream
 };
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(RDG_BLOCK, 2) preprocess_bwd_kernel(const PreB
             int64_t gi;
             if (chunk_slot(chunk_nx, gi)) { radius_pf = p.geom.radii[gi]; clamped_pf = p.geom.clamped[gi]; }
         }
+        if (p.l2_prefetch && chunk_nx < p.c_end && threadIdx.x < 8) rdg_prefetch_chunk_field(sc, chunk_nx, cs, threadIdx.x, p.acc);
         // the chunk after the next one (claimed by thread 0, published by the barrier below, read at the end of the iteration)
         if (queued && threadIdx.x == 0) q_s[q_par] = p.c_begin + (long long)atomicAdd(p.sm_queue, 1u);
 
@@ -662,6 +664,7 @@ extern "C" int rdg_preprocess_bwd(const RdgScene* scene, const RdgView* view, co
     const bool do_static = grads->models != 2, do_dynamic = grads->models != 1;
     p.sm_queue = nullptr;
     p.sm_limit = 0;
+    p.l2_prefetch = rdg_tunable(RDG_TUN_L2_PREFETCH) != 0 ? 1 : 0;
     p.c_begin = do_static ? 0 : cs_h;
     p.c_end = do_dynamic ? cs_h + cd_h : cs_h;
     RDG_CHECK_ARG(grads->parts >= 0 && grads->part >= 0 && (grads->parts == 0 ? grads->part == 0 : grads->part < grads->parts), "bad part / parts");

@@ -27,6 +27,7 @@ struct PreFwdParams {
     RdgGeom geom;
     int use_tma;
     int diff_smem;   // B(t) - table rows staged in shared memory (rdg_stage_diff); the launcher sized the buffer
+    int l2_prefetch; // next chunk's parameter rows prefetched into L2 (cp.async.bulk.prefetch.L2)
 };
 
 // Measured alternatives that did NOT help (B200, C4, profiles/r01_ab_v12_*.json, r01_ab_v13_*.json): double-buffering the SH
@@ -66,6 +67,8 @@ __global__ void __launch_bounds__(RDG_BLOCK) preprocess_fwd_kernel(const PreFwdP
         const int64_t lbase = (dyn ? chunk - cs : chunk) * RDG_BLOCK;
         const int64_t n_set = dyn ? sc.n_dynamic : sc.n_static;
         const int cnt = (int)min((int64_t)RDG_BLOCK, n_set - lbase);
+        if (p.l2_prefetch && chunk + gridDim.x < cs + cd && threadIdx.x < 8)
+            rdg_prefetch_chunk_field(sc, chunk + gridDim.x, cs, threadIdx.x, nullptr);
 
         // ---- stage this chunk's higher-order SH rows in shared memory ----
         bool tma = false;
@@ -159,10 +162,10 @@ __global__ void __launch_bounds__(RDG_BLOCK) preprocess_fwd_kernel(const PreFwdP
                 rgb[0] = b[0] * dc0; rgb[1] = b[0] * dc1; rgb[2] = b[0] * dc2;
                 const float* rest = sh_s + threadIdx.x * SH_ROW;
 #pragma unroll
-                for (int k = 1; k < K; ++k) {
-                    rgb[0] += b[k] * rest[(k - 1) * 3 + 0];
-                    rgb[1] += b[k] * rest[(k - 1) * 3 + 1];
-                    rgb[2] += b[k] * rest[(k - 1) * 3 + 2];
+                for (int k = 1; k < K; ++k) {   // explicit FMAs (-fmad=false TU): the colour feeds no integer output
+                    rgb[0] = fmaf(b[k], rest[(k - 1) * 3 + 0], rgb[0]);
+                    rgb[1] = fmaf(b[k], rest[(k - 1) * 3 + 1], rgb[1]);
+                    rgb[2] = fmaf(b[k], rest[(k - 1) * 3 + 2], rgb[2]);
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -234,6 +237,7 @@ extern "C" int rdg_preprocess_fwd(const RdgScene* scene, const RdgView* view, co
     // TMA needs 16-byte aligned global sources; torch allocations are, arbitrary views may not be
     const bool aligned = (((uintptr_t)scene->st.sh_rest | (uintptr_t)scene->dy.sh_rest) & 15u) == 0;
     p.use_tma = aligned ? 1 : 0;
+    p.l2_prefetch = rdg_tunable(RDG_TUN_L2_PREFETCH) != 0 ? 1 : 0;
     size_t smem = (RDG_BLOCK * SH_ROW + RDG_NUM_BASIS_MAX * 7) * sizeof(float);
     // B(t) - table rows in shared memory when the whole table fits next to the SH rows with 2 CTAs per SM (T <= 140)
     p.diff_smem = 0;

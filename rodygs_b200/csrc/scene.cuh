@@ -9,6 +9,7 @@
 //                                                        to the normalised quaternion, not re-normalised)
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 struct RdgAct {
     float x, y, z;     // (deformed) mean
@@ -49,6 +50,9 @@ __device__ __forceinline__ void rdg_stage_diff(const RdgScene& sc, const float* 
 
 // delta[j] = sum_k c_k (B(t)[k][j] - table[ti][k][j]),  j = 0..6.  diff_s: rdg_stage_diff()'s copy, or NULL (then the
 // table row is gathered from global memory).  Same float operations either way: the results are bit-identical.
+// The accumulation is an explicit fmaf chain: the deformed mean is an INPUT of the bit-exact part of the forward pass (the
+// integer outputs are checked against the oracle run on the activated values the kernel itself produced), so it may be
+// fused - 112 instructions instead of 224 per dynamic Gaussian in the -fmad=false forward translation unit.
 __device__ __forceinline__ void rdg_deform_delta(const RdgScene& sc, const float* basis_t, int ti, const float* c, float* d,
                                                  const float* diff_s = nullptr) {
 #pragma unroll
@@ -63,7 +67,7 @@ __device__ __forceinline__ void rdg_deform_delta(const RdgScene& sc, const float
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 const int e = 4 * q + m;
-                d[e % 7] += c[e / 7] * r[m];
+                d[e % 7] = fmaf(c[e / 7], r[m], d[e % 7]);   // explicit FMA: the forward TU is built with -fmad=false
             }
         }
     } else if (sc.num_basis == RDG_NUM_BASIS_MAX) {
@@ -75,13 +79,13 @@ __device__ __forceinline__ void rdg_deform_delta(const RdgScene& sc, const float
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 const int e = 4 * q + m;          // e = k*7 + j, compile-time after unrolling
-                d[e % 7] += c[e / 7] * (basis_t[e] - r[m]);
+                d[e % 7] = fmaf(c[e / 7], basis_t[e] - r[m], d[e % 7]);
             }
         }
     } else {
         for (int k = 0; k < sc.num_basis; ++k)
 #pragma unroll
-            for (int j = 0; j < 7; ++j) d[j] += c[k] * (basis_t[k * 7 + j] - __ldg(row + k * 7 + j));
+            for (int j = 0; j < 7; ++j) d[j] = fmaf(c[k], basis_t[k * 7 + j] - __ldg(row + k * 7 + j), d[j]);
     }
 }
 
@@ -134,6 +138,31 @@ __device__ __forceinline__ void rdg_fetch(const RdgScene& sc, bool dyn, int64_t 
         a.qinv = 1.0f;
         a.op = o;
     }
+}
+
+// L2 prefetch (rdg_bulk_prefetch_l2, tma.cuh) of the parameter rows of 256-Gaussian chunk `chunk`: thread f = 0..7 of the CTA
+// takes one field.  cs = number of static chunks.  acc: the blend backward's accumulator rows (backward pass) or NULL.
+__device__ __forceinline__ void rdg_prefetch_chunk_field(const RdgScene& sc, int64_t chunk, int64_t cs, int f, const float* acc) {
+    const bool dyn = chunk >= cs;
+    const RdgSet& set = dyn ? sc.dy : sc.st;
+    const int64_t lbase = (dyn ? chunk - cs : chunk) * RDG_BLOCK;
+    const int64_t n_set = dyn ? sc.n_dynamic : sc.n_static;
+    const int64_t cnt = min((int64_t)RDG_BLOCK, n_set - lbase);
+    if (cnt <= 0) return;
+    const char* ptr = nullptr;
+    int64_t bytes = 0;
+    switch (f) {
+        case 0: ptr = (const char*)(set.xyz + lbase * 3); bytes = cnt * 12; break;
+        case 1: ptr = (const char*)(set.scaling + lbase * 3); bytes = cnt * 12; break;
+        case 2: ptr = (const char*)(set.rotation + lbase * 4); bytes = cnt * 16; break;
+        case 3: ptr = (const char*)(set.opacity + lbase); bytes = cnt * 4; break;
+        case 4: if (set.sh_dc && set.sh_dc_stride == 3) { ptr = (const char*)(set.sh_dc + lbase * 3); bytes = cnt * 12; } break;
+        case 5: if (acc) { ptr = (const char*)(acc + ((dyn ? sc.n_static : 0) + lbase) * 12); bytes = cnt * 48; } break;
+        case 6: if (dyn && sc.raw && sc.use_deform && sc.motion_coeff) { ptr = (const char*)(sc.motion_coeff + lbase * sc.num_basis); bytes = cnt * sc.num_basis * 4; } break;
+        default: if (dyn && sc.raw && sc.use_deform && sc.time_ind) { ptr = (const char*)(sc.time_ind + lbase); bytes = cnt * 4; } break;
+    }
+    bytes &= ~(int64_t)15;
+    if (ptr && bytes > 0 && ((uintptr_t)ptr & 15u) == 0) rdg_bulk_prefetch_l2(ptr, (uint32_t)bytes);
 }
 
 // Everything downstream of the activated parameters that both passes need.

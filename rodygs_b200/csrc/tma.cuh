@@ -48,3 +48,11 @@ __device__ __forceinline__ void rdg_bulk_store(void* gmem_dst, const void* smem_
 
 // wait until the bulk stores of this thread have finished READING their shared-memory source
 __device__ __forceinline__ void rdg_bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// L2 prefetch of a contiguous global range by ONE instruction (no registers, no shared memory, no completion to wait for):
+// gmem must be 16-byte aligned and bytes a multiple of 16.  The persistent per-Gaussian kernels issue it for the NEXT chunk's
+// parameter rows while the current chunk is computed, so that the dependent scalar loads of the next chunk find their lines
+// in L2 (~1/3 of the DRAM latency they were exposed to: ncu r02, 47 % of the warp stalls of preprocess_bwd were long-scoreboard).
+__device__ __forceinline__ void rdg_bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
