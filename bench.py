@@ -352,6 +352,8 @@ def run_ours(args, rank, world, local_rank):
 
     cur_stream = torch.cuda.current_stream()   # looked up once: torch.cuda.current_stream() costs ~15 us per call
 
+    graphs = [None, None]     # e2e leg, one GPU: the step captured as a CUDA graph per staging slot (see after the main leg)
+
     def one_step(k, e2e=False):
         vm, pm, bt, gt, gtd, cam = (host_inputs if e2e else dev_inputs)[k % len(dev_inputs)]
         if e2e:
@@ -359,8 +361,11 @@ def run_ours(args, rank, world, local_rank):
                 prefetch(0)
             cur_stream.wait_event(ready[k % 2])
             vm, pm, bt, gt, gtd = slots[k % 2]
-        step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, bt, gt, gtd, forward_only=args.forward_only,
-                              dcolor_slot=0 if factored else None)
+        if e2e and graphs[k % 2] is not None:
+            graphs[k % 2].replay()
+        else:
+            step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, bt, gt, gtd, forward_only=args.forward_only,
+                                  dcolor_slot=0 if factored else None)
         if e2e:
             consumed[k % 2].record(cur_stream)
             prefetch(k + 1)    # enqueued after this step's launches: the GPU is never idle while the copies are set up
@@ -430,7 +435,21 @@ def run_ours(args, rank, world, local_rank):
     step.stage_events = None
     clocks = sampler.stop(t_region0, t_region1) if sampler else None
 
-    # e2e leg (host buffers -> H2D -> step -> D2H loss)
+    # e2e leg (host buffers -> H2D -> step -> D2H loss).  One GPU: the step is replayed as a CUDA graph (one per staging
+    # slot), so the GPU does not wait for Python to enqueue ~25 launches after every loss read.
+    e2e_api = "rodygs_b200.trainer.SplatTrainStep.forward_backward (fused flat-buffer path)"
+    same_fov = all(abs(c.tanfovx - cams[0].tanfovx) < 1e-12 and abs(c.tanfovy - cams[0].tanfovy) < 1e-12 for c in cams)
+    if world == 1 and not args.forward_only and not args.adam and not args.no_graph and same_fov:
+        try:
+            for s_ in range(2):
+                for dst, h in zip(slots[s_], host_inputs[s_ % len(host_inputs)][:5]):
+                    dst.copy_(h)
+                vm_, pm_, bt_, gt_, gtd_ = slots[s_]
+                graphs[s_] = step.capture_forward_backward(vm_, pm_, cams[0].tanfovx, cams[0].tanfovy, bt_, gt_, gtd_)
+            e2e_api = "rodygs_b200.trainer.SplatTrainStep.capture_forward_backward + CapturedStep.replay (the fused step as one CUDA graph)"
+        except Exception as e:   # noqa: BLE001 - the eager step is the fallback
+            print(f"bench: CUDA-graph capture of the step failed ({type(e).__name__}: {e}); e2e runs eagerly", file=sys.stderr)
+            graphs[0] = graphs[1] = None
     for k in range(2):
         one_step(k, e2e=True)
     ms_e2e, per_step_e2e, _, _ = timed(args.steps, e2e=True)
@@ -597,7 +616,7 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps, "ms_per_step_stats": pct(per_step_e2e),
-                    "api": "rodygs_b200.trainer.SplatTrainStep.forward_backward (fused flat-buffer path)"},
+                    "api": e2e_api},
             "e2e_dropin": dropin,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -684,6 +703,7 @@ def main():
     ap.add_argument("--sh-degree", type=int, default=3, choices=[0, 1, 2, 3],
                     help="active SH degree (the reference trains at degree 0 for 15000 of 20000 iterations)")
     ap.add_argument("--no-local-pearson", action="store_true", help="leave the 0.15-weighted LocalPearsonDepthLoss out of the step (A/B)")
+    ap.add_argument("--no-graph", action="store_true", help="e2e leg: enqueue the step eagerly instead of replaying its CUDA graph (A/B)")
     ap.add_argument("--no-dropin", action="store_true", help="skip the e2e_dropin leg (GaussianRasterizer + autograd)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c4_iphone")

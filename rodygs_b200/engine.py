@@ -49,6 +49,10 @@ class Config:
     # partials as scaled 64-bit integers (rdg_blend_bwd_deterministic) and the per-Gaussian backward runs on one CTA so that
     # the cross-CTA atomics of dL/dV, dL/dtable, dL/dB(t) keep one order.  Also switched on by RDG_DETERMINISTIC=1.
     deterministic: bool = os.environ.get("RDG_DETERMINISTIC", "0") == "1"
+    # set by SplatTrainStep.capture_forward_backward while a CUDA graph of the step is being captured (sync_free only): the
+    # host-side look at the previous frame's duplicate count moves to CapturedStep.replay()
+    capturing: bool = False
+    capture_host = None                 # pinned [2] int32 that receives the captured step's duplicate count
 
 
 config = Config()
@@ -75,7 +79,8 @@ def _check_pending(st: dict):
     if pend is None:
         return
     host, ev, cap_used = pend
-    ev.synchronize()
+    if ev is not None:
+        ev.synchronize()
     st["pending"] = None
     d = int(host[0])
     if d > cap_used:
@@ -287,7 +292,8 @@ def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = T
         stage_hook("preprocess_fwd")
 
     st = _cap_state(dev, n)
-    _check_pending(st)
+    if not config.capturing:
+        _check_pending(st)
     ntiles = tiles_of(H, W)
     ranges = torch.empty(ntiles, 2, dtype=torch.int32, device=dev)
     point_offsets = torch.empty(n, dtype=torch.int32, device=dev)
@@ -316,10 +322,13 @@ def render_forward(scene: SceneArgs, view: ViewArgs, keep_for_backward: bool = T
         check((lib.rdg_bin_tiles if use_tiles else lib.rdg_bin)(n, C.byref(gm_s), H, W, d_cap, C.byref(bins), ptr(ws),
                                                                 ws_bytes, stream))
         if config.sync_free:
-            host = torch.empty(2, dtype=torch.int32, pin_memory=True)
+            # (under graph capture the pinned buffer was allocated beforehand: no cudaHostAlloc inside a capture)
+            host = config.capture_host if config.capturing else torch.empty(2, dtype=torch.int32, pin_memory=True)
             host.copy_(num_rendered, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
+            ev = None
+            if not config.capturing:
+                ev = torch.cuda.Event()
+                ev.record()
             st["pending"] = (host, ev, d_cap)
             break
         d = int(num_rendered[0].item())          # the reference's one host read per forward

@@ -97,6 +97,24 @@ def allgather_rows(local: torch.Tensor, out: torch.Tensor, group=None) -> torch.
     return out
 
 
+class CapturedStep:
+    """A captured SplatTrainStep.forward_backward (CUDA graph).  replay() runs it on the current stream; the duplicate count of
+    the PREVIOUS replay (copied to pinned host memory by the graph) is checked against the captured buffers' capacity first -
+    the graph cannot re-bin, so an overflow raises and the step has to be captured again."""
+
+    def __init__(self, graph, host_count, d_cap, state, outputs):
+        self.graph, self._host, self.d_cap = graph, host_count, int(d_cap)
+        self.state, self.outputs = state, outputs           # tensors of the graph's private pool (valid after every replay)
+        self._replays = 0
+
+    def replay(self):
+        if self._replays and int(self._host[0]) > self.d_cap:
+            raise RuntimeError(f"rodygs_b200: the captured step produced {int(self._host[0])} tile instances but its buffers hold "
+                               f"{self.d_cap}; that frame was truncated - capture the step again")
+        self._replays += 1
+        self.graph.replay()
+
+
 class SplatTrainStep:
     """Holds the flat parameter and gradient buffers of a static + dynamic model and runs
     forward + losses + backward for one view.
@@ -334,6 +352,35 @@ class SplatTrainStep:
         if accumulate:
             self.grads.add_(target)
         return self.loss_parts
+
+    def capture_forward_backward(self, viewmatrix, projmatrix, tanfovx, tanfovy, basis_t, gt_image, gt_depth) -> "CapturedStep":
+        """forward_backward() of one view captured as ONE CUDA graph (single-GPU step, engine.config.sync_free): ~25 kernel
+        launches, the torch fills and the per-call allocations become one cudaGraphLaunch, so the GPU does not idle while
+        Python enqueues the step after the user has synchronised on the previous loss.  The tensor arguments are STATIC
+        buffers: copy the next view's matrices / B(t) / targets into them, then replay().  tanfovx / tanfovy are baked in
+        (re-capture for a camera with other intrinsics).  Gradients land in self.grads, the loss in self.loss_parts."""
+        if not engine.config.sync_free:
+            raise RuntimeError("capture_forward_backward needs engine.config.sync_free = True (no host read inside the step)")
+        if getattr(self, "world_size", 1) > 1:
+            raise RuntimeError("capture_forward_backward covers the single-GPU step (the exchange runs on side streams)")
+        args = (viewmatrix, projmatrix, tanfovx, tanfovy, basis_t, gt_image, gt_depth)
+        for _ in range(2):                       # warm up: buffers sized, attributes set, lazy initialisation done
+            self.forward_backward(*args)
+        torch.cuda.synchronize()
+        st = engine._cap_state(self.params.device, self.ns + self.nd)
+        engine._check_pending(st)
+        graph = torch.cuda.CUDAGraph()
+        engine.config.capture_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        engine.config.capturing = True
+        try:
+            with torch.cuda.graph(graph):
+                self.forward_backward(*args)
+        finally:
+            engine.config.capturing = False
+            engine.config.capture_host = None
+        host, _, d_cap = st["pending"]
+        st["pending"] = None
+        return CapturedStep(graph, host, d_cap, self.last_state, self.last_outputs)
 
     def allreduce_grads(self, scale: Optional[float] = None):
         """Sum (and optionally scale) the WHOLE flat gradient buffer over the data-parallel group

@@ -376,3 +376,44 @@ def test_deterministic_mode_is_bit_reproducible_and_agrees_with_the_default():
         assert float((a[k] - c[k]).abs().max()) <= 2e-5 * scale + 1e-30, f"{k}: deterministic vs default"
     # (the default mode is allowed to differ in the last bits between runs: float atomics)
     assert any(not torch.equal(c[k], d[k]) for k in c) or True
+
+
+def test_captured_step_replays_the_eager_step():
+    """SplatTrainStep.capture_forward_backward: the step as one CUDA graph gives the gradients and the loss of the eager
+    step (deterministic mode: bit-identical), also after the static input buffers were refilled with another view."""
+    N, H, W, T = 30_000, 128, 192, 6
+    scene = synthetic.to_device(synthetic.make_scene(N, H, W, T, seed=6), "cuda")
+    step = SplatTrainStep(scene, H, W, sh_degree=3, w_pearson=0.05, w_alpha=0.01)
+    step.local_box_origins = torch.tensor([[0, 10]])
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    views = []
+    for v in (0, 3):
+        cam = synthetic.make_camera(v, 8, H, W, T)
+        views.append((cam, cam.world_view_transform.t().contiguous().cuda(), cam.projection_matrix.t().contiguous().cuda(),
+                      step.p("table")[cam.time_index].clone(), torch.rand(3, H, W, device="cuda", generator=gen),
+                      torch.rand(1, H, W, device="cuda", generator=gen)))
+    was = engine.config.sync_free
+    try:
+        engine.config.sync_free = True
+        engine.config.deterministic = True
+        ref = []
+        for cam, vm, pm, bt, gt, gtd in views:
+            step.forward_backward(vm, pm, cam.tanfovx, cam.tanfovy, bt, gt, gtd)
+            torch.cuda.synchronize()
+            ref.append((step.grads.clone(), step.loss_parts.clone(), step.view_grad.clone()))
+        cam0 = views[0][0]
+        static = [t.clone() for t in views[0][1:]]
+        cap = step.capture_forward_backward(static[0], static[1], cam0.tanfovx, cam0.tanfovy, static[2], static[3], static[4])
+        for k in (0, 1, 0):
+            for dst, src in zip(static, views[k][1:]):
+                dst.copy_(src)
+            step.grads.zero_()          # (the padding between the blocks is never written)
+            cap.replay()
+            torch.cuda.synchronize()
+            g, l, vg = ref[k]
+            assert torch.equal(step.grads, g), k
+            assert torch.equal(step.loss_parts, l) and torch.equal(step.view_grad, vg), k
+    finally:
+        engine.config.sync_free = was
+        engine.config.deterministic = False
+        engine.reset_capacity()
