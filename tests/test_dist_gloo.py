@@ -66,7 +66,7 @@ def _worker(rank, world, port, ret):
             flat += _view_grads(sc, v, layout, total)
         allreduce_flat(flat, 1.0 / VIEWS)
         if rank == 0:
-            ret.put(flat.clone())
+            ret.put(flat.numpy().copy())   # by value: a torch tensor travels as a shared-memory handle that dies with this process
     finally:
         dist.destroy_process_group()
 
@@ -80,7 +80,7 @@ def test_view_sharded_allreduce_matches_sequential():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
     for p in procs:
         p.start()
-    got = ret.get(timeout=240)
+    got = torch.from_numpy(ret.get(timeout=240))
     for p in procs:
         p.join(timeout=180)
         assert p.exitcode == 0, f"worker exit code {p.exitcode}"
@@ -130,7 +130,7 @@ def _worker_factored(rank, world, port, ret):
             o, _ = layout[f"{tag}.features_rest"]
             flat[o:o + (hi_ - lo_) * 45] = g[lo_:hi_, 1:].reshape(-1)
         if rank == 0:
-            ret.put(flat.clone())
+            ret.put(flat.numpy().copy())   # by value: a torch tensor travels as a shared-memory handle that dies with this process
     finally:
         dist.destroy_process_group()
 
@@ -144,7 +144,7 @@ def test_factored_sh_exchange_matches_sequential():
     procs = [ctx.Process(target=_worker_factored, args=(r, 2, port, ret)) for r in range(2)]
     for p in procs:
         p.start()
-    got = ret.get(timeout=240)
+    got = torch.from_numpy(ret.get(timeout=240))
     for p in procs:
         p.join(timeout=180)
         assert p.exitcode == 0, f"worker exit code {p.exitcode}"
@@ -174,7 +174,7 @@ def _worker_stats(rank, world, port, ret):
         st.denom.copy_(torch.randint(0, 3, (50,), generator=g).float())
         st.max_radii2D.copy_(torch.randint(0, 40, (50,), generator=g).float())
         st.all_reduce(None)
-        ret.put((rank, st.grad_accum.clone(), st.denom.clone(), st.max_radii2D.clone()))
+        ret.put((rank, st.grad_accum.numpy().copy(), st.denom.numpy().copy(), st.max_radii2D.numpy().copy()))   # by value
     finally:
         dist.destroy_process_group()
 
@@ -188,7 +188,7 @@ def test_densification_statistics_are_rank_consistent_on_the_default_group():
     procs = [ctx.Process(target=_worker_stats, args=(r, 2, port, ret)) for r in range(2)]
     for p in procs:
         p.start()
-    got = dict((r[0], r[1:]) for r in (ret.get(timeout=120), ret.get(timeout=120)))
+    got = dict((r[0], tuple(torch.from_numpy(a) for a in r[1:])) for r in (ret.get(timeout=120), ret.get(timeout=120)))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
