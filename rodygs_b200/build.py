@@ -30,7 +30,6 @@ SOURCES = {
     "binning.cu": ["-fmad=false"],
     "binning_tiles.cu": ["-fmad=false"],
     "blend.cu": [],
-    "blend_r1.cu": [],
     "preprocess_bwd.cu": [],
     "sh_grad_views.cu": [],
     "exchange.cu": [],

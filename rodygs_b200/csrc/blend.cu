@@ -1,7 +1,8 @@
 // Front-to-back alpha blend (forward) and reverse-order backward over the depth-sorted per-tile lists.
 // SURVEY.md §8 rows a9 / a10; spec: SURVEY.md App. A.4-A.6 == oracle/splat_oracle.py::blend (+ autograd).
 //
-// B200 mapping, round 2 (profiles/README.md has the measured history; round 1 lives in blend_r1.cu for A/B):
+// B200 mapping, round 2 (profiles/README.md has the measured history; the round-1 kernels are kept OUT of the product library as
+// tools/legacy/blend_r1.cu for reference):
 //  * The 16x16 tile is cut into sixteen 4x4-pixel sub-tiles.  A WARP owns one REGION = a 16x8 half tile = eight
 //    sub-tiles; four lanes own one sub-tile and every lane owns one COLUMN of four pixels, so the record a lane
 //    fetches from shared memory, the column offset dx and the x-half of the conic are used four times, and the
@@ -56,10 +57,6 @@
 #ifndef BLEND_WARPS
 #define BLEND_WARPS 2           // warps per CTA; every warp blends one region on its own (no block-level synchronisation)
 #endif
-
-int rdg_blend_fwd_r1(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view, const RdgImage* out, void* stream);
-int rdg_blend_bwd_r1(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view, const RdgImage* fwd,
-                     const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, float* acc, void* stream);
 
 struct __align__(16) StagedW {      // one per warp
     float4 a[2][NSLOT];             // px, py, A, B          (double buffered: chunk k+1 lands while chunk k is blended)
@@ -836,15 +833,8 @@ __global__ void __launch_bounds__(32 * BLEND_WARPS, BWD_MINB) blend_bwd_kernel(
     rdg_cp_wait_all();
 }
 
-// RDG_BLEND_R1=1 selects the round-1 kernels (A/B measurements only)
-static bool rdg_use_r1() {
-    static const bool v = [] { const char* e = getenv("RDG_BLEND_R1"); return e && e[0] == '1'; }();
-    return v;
-}
-
 extern "C" int rdg_blend_fwd(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view,
                              const RdgImage* out, void* stream) {
-    if (rdg_use_r1()) return rdg_blend_fwd_r1(n, geom, bins, view, out, stream);
     RDG_CHECK_ARG(geom && bins && view && out, "null argument");
     RDG_CHECK_ARG(out->color && out->depth && out->alpha && out->final_T && out->n_contrib, "null image buffer");
     RDG_CHECK_ARG(view->bg, "null background");
@@ -867,7 +857,6 @@ extern "C" int rdg_blend_fwd(int64_t n, const RdgGeom* geom, const RdgBins* bins
 extern "C" int rdg_blend_bwd(int64_t n, const RdgGeom* geom, const RdgBins* bins, const RdgView* view,
                              const RdgImage* fwd, const float* dL_dcolor, const float* dL_ddepth,
                              const float* dL_dalpha, float* acc, void* stream) {
-    if (rdg_use_r1()) return rdg_blend_bwd_r1(n, geom, bins, view, fwd, dL_dcolor, dL_ddepth, dL_dalpha, acc, stream);
     RDG_CHECK_ARG(geom && bins && view && fwd && acc, "null argument");
     RDG_CHECK_ARG(fwd->final_T && fwd->n_contrib, "null forward state");
     RDG_CHECK_ARG(bins->region_ids && bins->region_masks && bins->region_count && bins->region_stride > 0, "null region-list buffer");

@@ -26,7 +26,6 @@ def main():
                 print(r.stdout, r.stderr); raise SystemExit(1)
             for l in (r.stdout + r.stderr).splitlines():
                 if "Used" in l or "spill" in l or "Compiling entry" in l:
-                    if "blend_r1" in l: continue
                     print("   ", l.strip()[:150])
         objs.append(obj)
     out = os.path.join(vdir, f"lib_{name}.so")

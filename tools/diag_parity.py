@@ -34,6 +34,6 @@ N = 62745
 sc = synthetic.make_scene(N, 256, 256, T, seed=0)
 cam = synthetic.make_camera(0, 8, 256, 256, T)
 acts = helpers.activated_concat(sc, cam)
-run([a.detach() for a in acts], cam, 256, 256, torch.zeros(3), 1.0, "window " + os.environ.get("RDG_BLEND_R1", "new"))
+run([a.detach() for a in acts], cam, 256, 256, torch.zeros(3), 1.0, "window")
 acts, cam = tg._adversarial("needle", 300, 112, 176, seed=len("needle") * 1000 + 300)
-run(acts, cam, 112, 176, torch.tensor([0.1, 0.2, 0.3]), 3.0, "needle x3 " + os.environ.get("RDG_BLEND_R1", "new"))
+run(acts, cam, 112, 176, torch.tensor([0.1, 0.2, 0.3]), 3.0, "needle x3")

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One development iteration on the GPU box: parity tests, bench (optionally A/B against an env switch),
 # launch list and an ncu capture of chosen kernels exported to CSV on the box.
-#   TESTS   pytest -k expression (default: all gpu tests; "none" skips)   AB_ENV  e.g. "RDG_BLEND_R1=1": second bench run
+#   TESTS   pytest -k expression (default: all gpu tests; "none" skips)   AB_ENV  e.g. "RDG_L2_PREFETCH=1": second bench run
 #   NCU_K   regex of kernels to capture with --set full (empty: skip)      NCU_S / NCU_C   skip / count
 #   BENCH_ARGS  extra bench flags      LAUNCH_LIST=1  per-launch time list
 mkdir -p gpurun_out

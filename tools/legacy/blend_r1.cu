@@ -1,4 +1,4 @@
-// ROUND-1 VERSION, kept only for A/B measurements during the round-2 rewrite (RDG_BLEND_R1=1); see blend.cu.
+// ROUND-1 VERSION of the blend kernels, kept for reference only: NOT part of the product library (rodygs_b200/build.py does not compile it).
 // Front-to-back alpha blend (forward) and reverse-order backward over the
 // depth-sorted per-tile lists.  SURVEY.md §8 rows a9 / a10; spec: SURVEY.md
 // App. A.4-A.6 == oracle/splat_oracle.py::blend (+ autograd).
