@@ -313,8 +313,9 @@ def run_ours(args, rank, world, local_rank):
     # every rank needs the view matrix and B(t) of every rank's view of the step (rank-major order)
     factored = world > 1 and not args.plain_allreduce and not args.forward_only
     if args.bwd_parts < 0:
-        # measured (profiles/README.md): pipelining the exchange pays on 2 GPUs (2.76 vs 2.86 ms/step), not on 8 (3.03-3.10 vs 2.94-2.98)
-        args.bwd_parts, args.bwd_order, args.bwd_parts_static = (4, "dst", 1) if world == 2 else (0, args.bwd_order, args.bwd_parts_static)
+        # measured (profiles/README.md): pipelining the exchange pays on 2 GPUs (2.76 vs 2.86 ms/step) and on 4 (2.80 vs 2.87), not on 8
+        # (3.03-3.10 vs 2.94-2.98: the NVLink ingress is busy for the whole tail either way)
+        args.bwd_parts, args.bwd_order, args.bwd_parts_static = (4, "dst", 1) if world <= 4 else (0, args.bwd_order, args.bwd_parts_static)
     all_vm, all_bt = [], []
     if factored:
         step.enable_factored_exchange(views_per_rank=1, world_size=world, copy_engine_gather=not args.nccl_gather,
@@ -727,7 +728,7 @@ def main():
                     help="N>1: size the persistent backward grids for 148 - sm_reserve SMs instead of the SM-partitioned chunk queue (A/B)")
     ap.add_argument("--bwd-parts", type=int, default=-1,
                     help="N>1, --allreduce multimem: launches of the dynamic model's per-Gaussian backward (pipelined exchange); 0: one bucket per model; "
-                         "-1 (default): the measured best - pipelined (4 dynamic launches, static, dL/dtable) on 2 GPUs, one bucket per model on 4 / 8")
+                         "-1 (default): the measured best - pipelined (4 dynamic launches, static, dL/dtable) on 2 / 4 GPUs, one bucket per model on 8")
     ap.add_argument("--allreduce", default="multimem", choices=["nccl", "multimem", "symm_op"],
                     help="N>1: all-reduce of the non-SH gradient range: NCCL, the in-switch kernel rdg_allreduce_multimem, or torch's symm_mem op")
     ap.add_argument("--allreduce-ctas", type=int, default=32)
