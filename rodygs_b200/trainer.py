@@ -499,9 +499,10 @@ class SplatTrainStep:
         self._ev_piece = {}
         self._buckets_started = 0
         # pipelined exchange (in-switch all-reduce only: the pieces are structure-of-arrays slices, one launch each)
-        self._bwd_plan, self._bwd_pieces = None, None
+        self._bwd_plan, self._bwd_pieces, self._bwd_final = None, None, None
         if self._bucketed and self._ar_mode == "multimem" and int(bwd_parts) > 0:
             self._bwd_plan, self._bwd_pieces = self._make_bwd_plan(int(bwd_parts), bwd_order, max(1, int(bwd_parts_static)))
+            self._bwd_final = [p[4] for p in self._bwd_plan if self._bwd_pieces[p[4]]][-1]
         self._sm_queue = torch.zeros(8, dtype=torch.int32, device=self.dev)
         if self._bucketed:
             _lib.set_tunable("sm_reserve", int(sm_reserve))
@@ -600,7 +601,8 @@ class SplatTrainStep:
                 lo, hi = self._buckets[piece]
                 self._allreduce_range(lo, hi)
             elif self._bwd_pieces[piece]:
-                self._allreduce_ranges(self._bwd_pieces[piece], final=(piece == self._bwd_plan[-1][4]))
+                # (a piece of a model with fewer chunks than pieces is empty; the LAST piece with ranges closes the step)
+                self._allreduce_ranges(self._bwd_pieces[piece], final=(piece == self._bwd_final))
         self._buckets_started += 1
 
     def _allreduce_ranges(self, ranges, final: bool):

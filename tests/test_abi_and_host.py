@@ -152,3 +152,51 @@ def test_tunables_are_validated_and_settable_without_a_gpu():
         _lib.set_tunable(name, default)
     with pytest.raises(RuntimeError, match="unknown tunable"):
         _lib.set_tunable("nope", 0)
+
+
+def test_pipelined_exchange_plan_tiles_the_reduced_range_exactly_once():
+    """Host logic of the pipelined data-parallel exchange (SplatTrainStep._make_bwd_plan / _piece_ranges), which needs no GPU: for
+    ragged Gaussian counts, every order and several piece counts, the float ranges all-reduced after the launches are 16-byte
+    aligned, disjoint, and together cover every gradient float in front of the SH blocks; the launch list matches
+    RdgSceneGrad.models / part / parts / dtable_mode (dL/dtable exactly once, after every dynamic piece)."""
+    import itertools
+    from rodygs_b200.trainer import SplatTrainStep, flat_layout, sh_start
+    for (ns, nd, pd, ps) in ((1000, 777, 4, 2), (300_001, 299_999, 3, 1), (255, 257, 2, 2), (5000, 4097, 1, 1)):
+        step = object.__new__(SplatTrainStep)               # the methods under test only read these attributes
+        step.ns, step.nd, step.num_basis = ns, nd, 16
+        step.layout, total = flat_layout(ns, nd, 16, 12)
+        n_plain = sh_start(step.layout)
+        for order in ("sdt", "dst", "dts"):
+            plan, pieces = step._make_bwd_plan(pd, order, ps)
+            names = [p[4] for p in plan]
+            assert len(set(names)) == len(names) and set(names) == set(pieces)
+            assert [p for p in plan if p[3] == 2] == [(2, 0, 1, 2, "table")]                 # the dL/dtable reduction: once
+            assert all(p[3] == 1 for p in plan if p[4] != "table")                           # the per-Gaussian launches skip it
+            dyn = [i for i, p in enumerate(plan) if p[4].startswith("dynamic.")]
+            assert [plan[i][1:3] for i in dyn] == [(k, pd) for k in range(pd)]
+            assert max(dyn) < names.index("table")
+            assert [p[1:3] for p in plan if p[4].startswith("static.")] == [(k, ps) for k in range(ps)]
+            for name in names:
+                for lo, ln in pieces[name]:
+                    assert lo % 4 == 0 and ln % 4 == 0 and ln > 0 and lo + ln <= n_plain
+            # interval arithmetic: the sorted ranges must not overlap and must contain every parameter block
+            ivs = sorted((lo, lo + ln) for name in names for lo, ln in pieces[name])
+            assert all(a[1] <= b[0] for a, b in zip(ivs, ivs[1:])), (ns, nd, order)
+            for field, (off, shp) in step.layout.items():
+                if off >= n_plain:
+                    continue
+                numel = 1
+                for d in shp:
+                    numel *= d
+                assert any(lo <= off and off + numel <= hi for lo, hi in _merge(ivs)), (field, ns, nd, order)
+            assert any(pieces[n] for n in names)            # (the last non-empty piece carries the step's closing barrier)
+
+
+def _merge(ivs):
+    out = []
+    for lo, hi in ivs:
+        if out and lo <= out[-1][1]:
+            out[-1][1] = max(out[-1][1], hi)
+        else:
+            out.append([lo, hi])
+    return out

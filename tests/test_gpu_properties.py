@@ -230,6 +230,7 @@ def test_backward_in_pieces_equals_one_launch_and_pieces_tile_the_reduced_range(
         step.enable_factored_exchange(views_per_rank=1, world_size=1)
         step.world_size, step._bucketed = 2, True      # take the data-parallel schedule on one GPU
         step._bwd_plan, step._bwd_pieces = step._make_bwd_plan(3)
+        step._bwd_final = "table"
         called = []
         step._after_model = called.append
         step._start_gather = lambda: None
