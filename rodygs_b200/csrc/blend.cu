@@ -1,8 +1,7 @@
 // Front-to-back alpha blend (forward) and reverse-order backward over the depth-sorted per-tile lists.
 // SURVEY.md §8 rows a9 / a10; spec: SURVEY.md App. A.4-A.6 == oracle/splat_oracle.py::blend (+ autograd).
 //
-// B200 mapping, round 2 (profiles/README.md has the measured history; the round-1 kernels are kept OUT of the product library as
-// tools/legacy/blend_r1.cu for reference):
+// B200 mapping, round 2 (profiles/README.md has the measured history of both rounds):
 //  * The 16x16 tile is cut into sixteen 4x4-pixel sub-tiles.  A WARP owns one REGION = a 16x8 half tile = eight
 //    sub-tiles; four lanes own one sub-tile and every lane owns one COLUMN of four pixels, so the record a lane
 //    fetches from shared memory, the column offset dx and the x-half of the conic are used four times, and the
