@@ -65,6 +65,28 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.rdg_adam(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-15, 1, 1.0, None) == -1
     with pytest.raises(RuntimeError, match="rodygs_b200 error -1"):
         _lib.check(lib.rdg_blend_fwd(0, None, None, None, None, None))
+    # the round-2 data-parallel entry points refuse bad arguments before they touch the device
+    assert lib.rdg_sh_adam_views(None, 3, 2, None, None, None, 1.0, None, None, 0.9, 0.999, 1e-15, None) == -1
+    sc = _lib.RdgScene()
+    sc.n_static = 8
+    one = (C.c_float * 4)()
+    assert lib.rdg_sh_adam_views(C.byref(sc), 3, 17, one, None, one, 1.0, None, None, 0.9, 0.999, 1e-15, None) == -1
+    assert b"n_views" in lib.rdg_last_error()
+    assert lib.rdg_sh_grad_views(C.byref(sc), 5, 2, one, None, one, 1.0, None, None, None, None) == -1
+    offs, lens = (C.c_int64 * 9)(*range(0, 36, 4)), (C.c_int64 * 9)(*([4] * 9))
+    assert lib.rdg_allreduce_multimem_ranges(one, offs, lens, 9, 0, 2, 0.5, 16, None) == -1
+    assert b"at most 8 ranges" in lib.rdg_last_error()
+    lens[0] = 6
+    assert lib.rdg_allreduce_multimem_ranges(one, offs, lens, 1, 0, 2, 0.5, 16, None) == -1      # not a multiple of 4 floats
+    assert lib.rdg_allreduce_multimem_ranges(one, offs, lens, 0, 3, 2, 0.5, 16, None) == -1      # rank >= world
+    assert lib.rdg_allreduce_multimem(None, 16, 0, 2, 0.5, 16, None) == -1
+    gr, vw, gm = _lib.RdgSceneGrad(), _lib.RdgView(), _lib.RdgGeom()
+    vw.sh_degree = 3
+    gr.part, gr.parts = 3, 2
+    assert lib.rdg_preprocess_bwd(C.byref(sc), C.byref(vw), C.byref(gm), one, C.byref(gr), None) == -1
+    assert b"part" in lib.rdg_last_error()
+    assert lib.rdg_set_tunable(b"l2_prefetch", 0) == 0 and lib.rdg_set_tunable(b"ar_unroll", 4) == 0
+    assert lib.rdg_set_tunable(b"no_such_knob", 1) == -1
 
 
 def test_settings_and_rasterizer_mirror_the_reference_interface():
