@@ -15,6 +15,7 @@ import ctypes as C
 import copy
 import math
 import os
+import sys
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -358,7 +359,8 @@ class SplatTrainStep:
         launches, the torch fills and the per-call allocations become one cudaGraphLaunch, so the GPU does not idle while
         Python enqueues the step after the user has synchronised on the previous loss.  The tensor arguments are STATIC
         buffers: copy the next view's matrices / B(t) / targets into them, then replay().  tanfovx / tanfovy are baked in
-        (re-capture for a camera with other intrinsics).  Gradients land in self.grads, the loss in self.loss_parts."""
+        (re-capture for a camera with other intrinsics, and after every densification: the graph holds the old buffers).
+        Gradients land in self.grads, the loss in self.loss_parts."""
         if not engine.config.sync_free:
             raise RuntimeError("capture_forward_backward needs engine.config.sync_free = True (no host read inside the step)")
         if getattr(self, "world_size", 1) > 1:
@@ -445,7 +447,7 @@ class SplatTrainStep:
                 self._ar_group_name = group.group_name
                 self._ar_rank = dist.get_rank(group)
             except Exception as e:   # noqa: BLE001 - the fallback is the NCCL ring
-                print(f"rodygs_b200: in-switch all-reduce unavailable ({type(e).__name__}: {e}); using NCCL")
+                print(f"rodygs_b200: in-switch all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
                 self._ar_mode = "nccl"
         self._symm = None
         self._mc_base = 0
@@ -473,7 +475,7 @@ class SplatTrainStep:
                 self._gather_streams = [torch.cuda.Stream(device=self.dev) for _ in range(max(1, int(gather_streams)))]
                 self._ev_push = [torch.cuda.Event() for _ in self._gather_streams]
             except Exception as e:   # noqa: BLE001 - any failure here only costs the overlap, never correctness
-                print(f"rodygs_b200: symmetric-memory gather unavailable ({type(e).__name__}: {e}); using NCCL all-gather")
+                print(f"rodygs_b200: symmetric-memory gather unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
                 self._symm = None
                 self.dcolor_all = None
         if self.dcolor_all is None:
